@@ -1,0 +1,206 @@
+"""Pins oracle/restate.py against fixtures frozen from the REAL reference (oracle/make_golden.py).
+
+CPU only.  The fixtures are outputs of the unmodified reference functions run in the dev
+container; inputs/weights are regenerated here from oracle.synth seeds.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from oracle.make_golden import SMALL, SMALL_D, small_parts
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def relmax(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+# ------------------------------------------------------------------ pooling (a3/a4)
+@pytest.mark.parametrize("t,d", [(100, 32), (10, 16), (2, 8), (5, 8)])
+@pytest.mark.parametrize("mode", ["temporal_spatial_pool", "spatial_pool", "none"])
+def test_pool_matches_reference(golden, t, d, mode):
+    g = golden(f"pool_{mode}_t{t}")
+    tok = synth.gen(f"pooltok{t}", (2, t, 256, d), 1.0, seed=5)
+    out = restate.pool_tokens(tok, mode)
+    assert list(out.shape[:2]) == list(g["mask_shape"])
+    if mode == "none":
+        out = out[:, ::97]
+    assert relmax(out, T(g["out"])) <= 1e-6
+    assert bool(g["mask_all_true"])
+
+
+def test_selected_frames_known_answers():
+    assert restate.selected_frames(100).tolist() == [0, 33, 66, 99]
+    assert restate.selected_frames(10).tolist() == [0, 3, 6, 9]
+    assert restate.selected_frames(2).tolist() == [0, 0, 1, 1]
+
+
+def test_pool_backward_matches_reference_autograd(golden):
+    g = golden("pool_bwd_t10")
+    dout = synth.gen("pooldout_bwd", (1, 266, 8), 1.0, seed=6)
+    d = restate.pool_tokens_backward(dout, 10)
+    assert relmax(d, T(g["dtok"])) <= 1e-6
+
+
+# ------------------------------------------------------------------ gather (a7)
+@pytest.mark.parametrize("name,shape,seedname,seed", [
+    ("gather_toy", None, None, None),
+    ("gather_rand", (4, 40, 64), "gather_hidden", 41),
+    ("gather_pos0", (1, 12, 16), "gather_hidden0", 42)])
+def test_gather_matches_reference(golden, name, shape, seedname, seed):
+    g = golden(name)
+    labels = T(g["labels"])
+    if shape is None:
+        hidden = torch.arange(2 * 10 * 8, dtype=torch.float32).reshape(2, 10, 8)
+    else:
+        hidden = synth.gen(seedname, shape, 1.0, seed=seed)
+    out, valid, rows = restate.gather_hand_traj(hidden, labels)
+    assert torch.equal(out, T(g["out"]))
+    # reference zeroes future_valid[i] in place for samples without hand tokens
+    assert torch.equal(valid, T(g["future_valid"]).all(dim=1))
+
+
+def test_gather_toy_known_answer():
+    hidden = torch.arange(2 * 10 * 8, dtype=torch.float32).reshape(2, 10, 8)
+    labels = torch.full((2, 10), -100, dtype=torch.int64)
+    labels[0, 5:9] = 32100
+    out, valid, rows = restate.gather_hand_traj(hidden, labels)
+    assert rows[0].tolist() == [4, 5, 6, 7] and rows[1].tolist() == [-1] * 4
+    assert out[0, 0].tolist() == [[32, 34, 36, 38], [40, 42, 44, 46], [48, 50, 52, 54], [56, 58, 60, 62]]
+    assert out[0, 1].tolist() == [[33, 35, 37, 39], [41, 43, 45, 47], [49, 51, 53, 55], [57, 59, 61, 63]]
+    assert valid.tolist() == [True, False] and float(out[1].abs().sum()) == 0.0
+
+
+def test_gather_wrong_count_raises():
+    labels = torch.full((1, 10), -100, dtype=torch.int64)
+    labels[0, 3:6] = 32100
+    with pytest.raises(RuntimeError):
+        restate.gather_hand_traj(torch.zeros(1, 10, 8), labels)
+
+
+# ------------------------------------------------------------------ small tower helpers
+@pytest.fixture(scope="module")
+def small():
+    sd, proj, emb = small_parts()
+    return sd, proj.weight.data, proj.bias.data, emb.weight.data
+
+
+def small_visual(small, px, mode="temporal_spatial_pool"):
+    sd, pw, pb, _ = small
+    return restate.pipeline(px, sd, pw, pb, mode, select_layer=-2, cfg=SMALL)[0]
+
+
+@pytest.mark.parametrize("arch", ["all", "temporal", "spatial", "temporal_spatial", "temporal_spatial_pool",
+                                  "spatial_pool"])
+def test_lita_videos_to_tokens(golden, small, arch):
+    g = golden(f"lita_{arch}")
+    px = synth.pixels((1, 6, 3, 224, 224), seed=7)
+    out = small_visual(small, px, arch)
+    assert list(out.shape) == list(g["shape"])
+    if arch == "all":
+        out = out[:, ::7]
+    assert relmax(out, T(g["out"])) <= 2e-5
+
+
+def test_v2t_pipeline(golden, small):
+    g = golden("v2t_pipeline")
+    px = synth.pixels((1, 6, 3, 224, 224), seed=7)
+    sd, pw, pb, _ = small
+    out, mask = restate.pipeline(px, sd, pw, pb, cfg=SMALL)
+    assert relmax(out, T(g["out"])) <= 2e-5
+    assert torch.equal(mask, T(g["mask"]))
+
+
+# ------------------------------------------------------------------ splice (a5/a6)
+def _check_splice(g, mask2, e2, l2, tol=2e-5):
+    ge = T(g["embeds"])
+    assert e2.shape == ge.shape
+    assert relmax(e2, ge) <= tol
+    if "labels" in g.files:
+        assert torch.equal(l2, T(g["labels"]))
+    else:
+        assert l2 is None
+    if "mask" in g.files:
+        gm = T(g["mask"])
+        assert str(mask2.dtype) == str(g["mask_dtype"]) if "mask_dtype" in g.files else True
+        assert torch.equal(mask2, gm)
+    else:
+        assert mask2 is None
+
+
+@pytest.mark.parametrize("name,is_eval", [
+    ("splice_hvlm_train_b3", False), ("splice_hvlm_train_padded", False), ("splice_hvlm_2hand", False),
+    ("splice_hvlm_0hand", False), ("splice_hvlm_ragged", False), ("splice_hvlm_eval_hands", True),
+    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False)])
+def test_splice_handsonvlm(golden, small, name, is_eval):
+    g = golden(name)
+    ids = T(g["ids"])
+    B = ids.shape[0]
+    px = synth.pixels((B, int(g["t"]), 3, 224, 224), seed=int(g["px_seed"]))
+    vis = small_visual(small, px)
+    mask = T(g["in_mask"]) if "in_mask" in g.files else None
+    labels = T(g["in_labels"]) if "in_labels" in g.files else None
+    fh = T(g["future_hands"]) if "future_hands" in g.files else None
+    m2, e2, l2 = restate.splice(ids, mask, labels, vis, small[3], "handsonvlm", future_hands=fh,
+                                is_evaluate=is_eval)
+    _check_splice(g, m2, e2, l2)
+    # text rows are exact copies of embedding rows, visual rows exact copies of pipeline() output
+    plan, _ = restate.splice_plan(ids[0], vis.shape[1])
+    for r, (kind, idx) in enumerate(plan):
+        if kind == 1:
+            assert torch.equal(e2[0, r], vis[0, idx])
+
+
+@pytest.mark.parametrize("name,pxshape,pxseed,cfg", [
+    ("splice_llava_cfg1", (1, 3, 224, 224), 12, "image"),
+    ("splice_llava_ragged", (2, 3, 224, 224), 13, "image"),
+    ("splice_llava_two_images", (2, 3, 224, 224), 14, "image"),
+    ("splice_llava_video", (1, 4, 3, 224, 224), 15, "video")])
+def test_splice_llava(golden, small, name, pxshape, pxseed, cfg):
+    g = golden(name)
+    sd, pw, pb, ew = small
+    px = synth.pixels(pxshape, seed=pxseed)
+    if cfg == "image":
+        feats = restate.tower_forward(px, sd, -2, SMALL)
+        vis = restate.project(feats, pw, pb)
+    else:
+        vis = small_visual(small, px)
+    ids = T(g["ids"])
+    m2, e2, l2 = restate.splice(ids, T(g["in_mask"]), T(g["in_labels"]), vis, ew, "llava")
+    assert bool(g["returned_ids_is_none"])
+    _check_splice(g, m2, e2, l2)
+
+
+def test_splice_cfg1_shapes(golden):
+    g = golden("splice_llava_cfg1")
+    assert g["embeds"].shape == (1, 311, SMALL_D)
+    assert (g["labels"][0, 35:291] == -100).all() and g["labels"][0, 34] != -100
+
+
+# ------------------------------------------------------------------ ViT-L/14 (a1; third-party HF CLIP)
+@pytest.mark.parametrize("profile,tol", [("hf", 2e-5), ("strong", 5e-5)])
+def test_vit_l14_restatement_matches_hf(golden, profile, tol):
+    g = golden(f"vit_l14_{profile}")
+    sd = synth.clip_state_dict(synth.VIT_L14, seed=0, profile=profile, n_layers=23)
+    px = synth.pixels((2, 3, 224, 224), seed=3)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    feats = restate.tower_forward(px, sd, -2)
+    assert feats.shape == (2, 256, 1024)
+    assert relmax(feats[:, ::8, ::4], T(g["sub"])) <= tol
+    assert relmax(feats.norm(dim=-1), T(g["norms"])) <= tol
+
+
+def test_pool_first_equals_project_first():
+    """mean o linear commute (SURVEY 8a notes): the CUDA path pools 1024-d features first."""
+    x = synth.gen("commute", (1, 10, 256, 64), 1.0, 3)
+    w = synth.gen("commute.w", (48, 64), 0.1, 3)
+    b = synth.gen("commute.b", (48,), 0.1, 3)
+    a = restate.pool_tokens(restate.project(x, w, b), "temporal_spatial_pool")
+    c = restate.project(restate.pool_tokens(x, "temporal_spatial_pool"), w, b)
+    assert relmax(c, a) <= 1e-5
