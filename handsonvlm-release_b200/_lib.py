@@ -1,0 +1,112 @@
+"""ctypes binding of libhvlm_b200.so -- the C ABI declared in include/hvlm_b200.h.
+
+The product path has NO fallback: if the shared library is missing or the device is not an sm_100 GPU the
+import of the compute ops fails loudly (RuntimeError), it never routes to torch eager or to oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhvlm_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "hvlm_b200.h")
+
+# enums (include/hvlm_b200.h)
+F32, BF16, F16 = 0, 1, 2
+POOL_MODES = {"temporal_spatial_pool": 0, "spatial_pool": 1, "temporal": 2, "spatial": 3, "temporal_spatial": 4}
+SPLICE_LLAVA, SPLICE_HANDSONVLM = 0, 1
+EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+PLAN_ERR_LEN_OVERFLOW, PLAN_ERR_IMG_OVERFLOW, PLAN_ERR_HAND_COUNT, PLAN_ERR_BAD_ID, PLAN_NOT_UNIFORM = 1, 2, 4, 8, 16
+VIT_MAX_LAYERS = 24
+
+p = C.c_void_p
+i32, i64, f32, sz = C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+
+class _Layer(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b",
+                                          "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class VitLayout(C.Structure):
+    _fields_ = [("patch_w", C.c_uint64), ("cls", C.c_uint64), ("pos", C.c_uint64), ("pre_ln_g", C.c_uint64),
+                ("pre_ln_b", C.c_uint64), ("layer", _Layer * VIT_MAX_LAYERS), ("total_bytes", C.c_uint64),
+                ("n_layers", C.c_int32), ("_pad", C.c_int32)]
+
+
+# symbol -> (restype, argtypes); must list every HVLM_API symbol of the header (tests/test_abi.py checks it)
+SIGNATURES = {
+    "hvlm_strerror": (C.c_char_p, [i32]),
+    "hvlm_abi_version": (i32, []),
+    "hvlm_device_check": (i32, [i32]),
+    "hvlm_gemm_bf16": (i32, [p, p, p, p, p, i32, i32, i32, i32, i32, p]),
+    "hvlm_vit_l14_layout": (i32, [i32, C.POINTER(VitLayout)]),
+    "hvlm_vit_l14_workspace_bytes": (sz, [i32]),
+    "hvlm_vit_l14_fwd": (i32, [p, i32, p, i32, i32, p, p, sz, p]),
+    "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
+    "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
+    "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, p, p, i32, p]),
+    "hvlm_vit_attention": (i32, [p, p, p, p, i32, p]),
+    "hvlm_pool_out_tokens": (i32, [i32, i32]),
+    "hvlm_pool_slowfast_fwd": (i32, [p, i32, i64, p, i32, i32, i32, i32, i32, p]),
+    "hvlm_pool_slowfast_bwd": (i32, [p, i32, p, i32, i32, i32, i32, i32, p]),
+    "hvlm_splice_count": (i32, [p, i32, i32, p, p]),
+    "hvlm_splice_plan": (i32, [p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p]),
+    "hvlm_splice_fwd": (i32, [p, p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p]),
+    "hvlm_splice_bwd": (i32, [p, i32, p, p, i32, i32, i32, i32, i32, p, p, p]),
+    "hvlm_hand_gather_fwd": (i32, [p, i32, p, i64, i32, i32, i32, p, p, p, p, p]),
+    "hvlm_hand_gather_bwd": (i32, [p, i32, p, i32, i32, i32, p, p]),
+    "hvlm_hand_gather_step": (i32, [p, i32, i32, i32, p, p]),
+    "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
+    "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libhvlm_b200.so failed")
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once) and declare every signature.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no non-CUDA fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if L.hvlm_abi_version() != 1:
+        raise RuntimeError("libhvlm_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def strerror(rc: int) -> str:
+    return lib().hvlm_strerror(rc).decode()
+
+
+class HvlmError(RuntimeError):
+    def __init__(self, what: str, rc: int):
+        super().__init__(f"{what} failed: {strerror(rc)} (status {rc})")
+        self.status = rc
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise HvlmError(what, rc)

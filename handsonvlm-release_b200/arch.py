@@ -1,0 +1,289 @@
+"""Drop-in mixins / helpers that keep the reference's call signatures for the visual-token path.
+
+  reference                                                             here
+  -----------------------------------------------------------------    -------------------------------
+  LlavaMetaForCausalLM          llava/model/llava_arch.py:73-234        LlavaMetaForCausalLM
+  LitaMetaForCausalLM           lita/model/lita_arch.py:17-85           LitaMetaForCausalLM
+  HandsOnVLMMetaForCausalLM     handsonvlm/model/handsonvlm_arch.py:8   HandsOnVLMMetaForCausalLM
+  VisualToTokenHelper           hoi_forecast/model/visual_to_tokens.py  VisualToTokenHelper
+  HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal
+                                handsonvlm/.../handsonvlm.py:212-451    HandsOnVLMMetaForCausalLM.prepare_inputs_...
+  inline <hand_traj> gather     handsonvlm/.../handsonvlm.py:146-187    gather_hand_traj_states
+
+A host model mixes these in exactly like the reference does and must provide ``get_model()`` (object with
+``vision_tower`` / ``get_vision_tower()``, ``mm_projector`` (nn.Linear) and ``embed_tokens`` (nn.Embedding)) and
+``config``.  All compute goes through ``ops`` (sm_100a kernels); nothing here falls back to torch eager.
+
+Order of operations: mean and Linear commute, so the video path pools the 1024-d ViT features FIRST and projects
+the 356 pooled rows (reference: projects 25 600 rows, then pools) -- identical up to fp32 rounding
+(SURVEY.md section 8a notes), 72x fewer projector FLOPs and a 4x smaller pooling read.  ``encode_images`` still
+returns every projected token, as its public signature requires.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .constants import HAND_TRAJ_TOKEN_ID, IGNORE_INDEX, IMAGE_TOKEN_INDEX
+from .tower import CLIPVisionTower
+
+_POOLED = ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temporal_spatial")
+
+
+def _project(projector, x2d: torch.Tensor) -> torch.Tensor:
+    """mm_projector (nn.Linear 1024 -> D, with bias) on the tcgen05 GEMM; output in the projector's dtype."""
+    w = projector.weight
+    out_f32 = w.dtype == torch.float32
+    y = ops.linear(x2d, w.to(torch.bfloat16), projector.bias.to(torch.float32), out_f32)
+    return y if y.dtype == w.dtype else y.to(w.dtype)
+
+
+def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str) -> torch.Tensor:
+    """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project)."""
+    assert images.ndim == 5, "multiple videos per sample not supported yet"
+    b, t = images.shape[:2]
+    flat = images.reshape(b * t, *images.shape[2:])
+    with torch.no_grad():
+        hidden = tower.forward_hidden(flat)                         # f32 [b*t,257,1024]
+    if mode in ("all", "none"):
+        feats = tower.feature_select(hidden, torch.bfloat16)        # [b*t,256(+1),1024]
+        tok = _project(projector, feats.reshape(-1, feats.shape[-1]))
+        return tok.reshape(b, t * feats.shape[1], -1)
+    if mode not in _POOLED:
+        raise ValueError(f"unknown video arch {mode}")
+    if tower.select_feature != "patch":
+        raise AssertionError(f"tokens.shape = {(b * t, 257, projector.out_features)}")   # reference asserts 256 tokens
+    pooled = ops.pool_slowfast(hidden, b, t, 257, 1, L.POOL_MODES[mode], True)   # bf16 [b,Nv,1024]
+    tok = _project(projector, pooled.reshape(-1, 1024))
+    return tok.reshape(b, pooled.shape[1], -1)
+
+
+class VisualToTokenHelper:
+    """Same constructor and ``pipeline`` contract as hoi_forecast/model/visual_to_tokens.py:7-37.
+    Supported: fuse_input_mode='origin' (the released config; the other modes are ablations on pre-extracted
+    lmdb features and are out of scope), video_compress_mode in {'temporal_spatial_pool','spatial_pool','none'}."""
+
+    def __init__(self, images_raw_encode, images_mm_projector, fuse_input_mode, video_compress_mode,
+                 mm_hidden_size, token_dim):
+        self.images_raw_encode = images_raw_encode
+        self.images_mm_projector = images_mm_projector
+        self.fuse_input_mode = fuse_input_mode
+        self.video_compress_mode = video_compress_mode
+        self.mm_hidden_size = mm_hidden_size
+        self.token_dim = token_dim
+        self.b = self.t = self.c = self.h = self.w = None
+
+    def pipeline(self, **kwargs):
+        images = kwargs.get("images")
+        if images is None:
+            raise ValueError("VisualToTokenHelper.pipeline: only images=... (fuse_input_mode='origin') is supported")
+        if self.fuse_input_mode != "origin":
+            raise ValueError(f"Unknown fuse_input_mode: {self.fuse_input_mode}")
+        if self.video_compress_mode not in ("temporal_spatial_pool", "spatial_pool", "none"):
+            raise ValueError(f"unsupported video_compress_mode: {self.video_compress_mode}")
+        self.b, self.t, self.c, self.h, self.w = images.shape
+        out = video_tokens(self.images_raw_encode, self.images_mm_projector, images, self.video_compress_mode)
+        n = out.shape[1]
+        assert out.shape == torch.Size([self.b, n, self.token_dim]), \
+            f"output_tokens.shape = {out.shape}, expected shape is {torch.Size([self.b, n, self.token_dim])}"
+        attention_mask = torch.ones(self.b, n, dtype=torch.bool, device=out.device)
+        return out, attention_mask
+
+    def encode_images(self, images):
+        assert images.shape == torch.Size([self.b, self.t, self.c, self.h, self.w]), images.shape
+        out = video_tokens(self.images_raw_encode, self.images_mm_projector, images, "none")
+        return out.reshape(self.b, self.t, -1, self.token_dim)
+
+    def compress_tokens(self, tokens, attention_mask):
+        mode = self.video_compress_mode
+        if mode == "none":
+            b, t, s, d = tokens.shape
+            return tokens.reshape(b, t * s, d), attention_mask.reshape(b, t * s)
+        out = ops.pool_tokens(tokens, mode)
+        return out, torch.ones(out.shape[:-1], dtype=torch.bool, device=out.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# splice
+# ------------------------------------------------------------------------------------------------
+def _raise_on_status(bits: int):
+    if bits & L.PLAN_ERR_BAD_ID:
+        raise IndexError("index out of range in self")                 # nn.Embedding's error for a bad token id
+    if bits & L.PLAN_ERR_IMG_OVERFLOW:
+        raise IndexError("index out of bounds: more image tokens than image features")
+    if bits & L.PLAN_ERR_HAND_COUNT:
+        raise AssertionError("number of <hand_traj> tokens does not match future_hands")
+    if bits & L.PLAN_ERR_LEN_OVERFLOW:
+        raise RuntimeError("hvlm splice: spliced sequence longer than the planned output (static splice "
+                           "contract violated: a sample has more than one image token)")
+
+
+def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual, visual_mask=None,
+                  future_hands=None, is_evaluate: bool = False):
+    """Core of both prepare_inputs_labels_for_multimodal variants -> (attention_mask', embeds, labels')."""
+    table = host.get_model().embed_tokens.weight
+    B, T = input_ids.shape
+    n_img, Nv, D = visual.shape
+    if visual.dtype != table.dtype:
+        visual = visual.to(table.dtype)
+    static = bool(getattr(host.config, "hvlm_static_splice", False))
+    counts = ops.splice_count(input_ids)
+    if static:
+        # collator contract (hybrid_dataset.py:155-158): exactly one image token per sample, equal T
+        Lout, uniform = T - 1 + Nv, True
+    else:
+        ks = counts.tolist()                                         # the ONE host sync of the general path
+        lens = [T + k * (Nv - 1) for k in ks]
+        Lout, uniform = max(lens), all(n == lens[0] for n in lens)
+    hand_mode, n_hand = 0, 0
+    if variant == L.SPLICE_HANDSONVLM:
+        if not is_evaluate:
+            if future_hands is None:
+                raise TypeError("'NoneType' object is not subscriptable")   # kwargs.get('future_hands')[batch_idx]
+            assert tuple(future_hands.shape[1:]) == (2, 4, 2), future_hands.shape
+            hand_mode, n_hand = 1, 4
+        elif future_hands is not None:
+            hand_mode, n_hand = 2, int(future_hands.shape[2])
+    src_index, hand_code, lens_d, hand_scale, status = ops.splice_plan(
+        input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand)
+    if not static:
+        _raise_on_status(int(status.item()))
+    else:
+        host._hvlm_splice_status = status                             # device flag; check lazily if wanted
+    embeds, new_labels, new_mask = ops.splice_gather(
+        src_index, hand_code, lens_d, hand_scale, input_ids, labels, attention_mask, table, visual, visual_mask,
+        future_hands if hand_mode else None, variant)
+    if labels is None:
+        new_labels = None
+    if attention_mask is None:
+        new_mask = None
+    elif variant == L.SPLICE_HANDSONVLM and not uniform:
+        # bug-compatible with handsonvlm.py:441: a ragged batch pads the MASK with IGNORE_INDEX in the labels' dtype
+        ar = torch.arange(Lout, device=new_mask.device).unsqueeze(0)
+        new_mask = torch.where(ar < lens_d.unsqueeze(1), new_mask.to(torch.int64),
+                               torch.full((), IGNORE_INDEX, dtype=torch.int64, device=new_mask.device))
+    elif attention_mask.dtype != torch.bool:
+        new_mask = new_mask.to(attention_mask.dtype)
+    return new_mask, embeds, new_labels
+
+
+class LlavaMetaForCausalLM(ABC):
+    """llava/model/llava_arch.py:73-234"""
+
+    @abstractmethod
+    def get_model(self):
+        pass
+
+    def get_vision_tower(self):
+        return self.get_model().get_vision_tower()
+
+    def encode_images(self, images):
+        """images [N,3,224,224] -> [N,256,D]  (llava_arch.py:81-93)"""
+        tower = self.get_model().get_vision_tower()
+        with torch.no_grad():
+            hidden = tower.forward_hidden(images)
+        feats = tower.feature_select(hidden, torch.bfloat16)
+        tok = _project(self.get_model().mm_projector, feats.reshape(-1, feats.shape[-1]))
+        return tok.reshape(feats.shape[0], feats.shape[1], -1)
+
+    def images_to_tokens(self, images):
+        if type(images) is list or images.ndim == 5:
+            concat_images = torch.cat([image for image in images], dim=0)
+            image_features = self.encode_images(concat_images)
+            split_sizes = [image.shape[0] for image in images]
+            image_features = torch.split(image_features, split_sizes, dim=0)
+            image_features = [x.flatten(0, 1) for x in image_features]
+        else:
+            image_features = self.encode_images(images)
+        return image_features
+
+    def visual_to_tokens(self, images):
+        return self.images_to_tokens(images)
+
+    def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images):
+        """llava_arch.py:110-234 (released flags: no <im_start>/<im_end>)."""
+        vision_tower = self.get_vision_tower()
+        if vision_tower is None or images is None or input_ids.shape[1] == 1:
+            if past_key_values is not None and vision_tower is not None and images is not None and input_ids.shape[1] == 1:
+                attention_mask = torch.ones((attention_mask.shape[0], past_key_values[-1][-1].shape[-2] + 1),
+                                            dtype=attention_mask.dtype, device=attention_mask.device)
+            return input_ids, attention_mask, past_key_values, None, labels
+        if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
+            raise NotImplementedError("mm_use_im_start_end splice variant is not part of the released config")
+        image_features = self.visual_to_tokens(images)
+        if isinstance(image_features, (list, tuple)):
+            if any(x.shape != image_features[0].shape for x in image_features):
+                raise NotImplementedError("per-image variable token counts are not supported by the splice kernel")
+            image_features = torch.stack(list(image_features), 0)
+        new_mask, embeds, new_labels = splice_tokens(self, L.SPLICE_LLAVA, input_ids, attention_mask, labels,
+                                                     image_features)
+        return None, new_mask, past_key_values, embeds, new_labels
+
+
+class LitaMetaForCausalLM(LlavaMetaForCausalLM):
+    """lita/model/lita_arch.py:17-85"""
+
+    def videos_to_tokens(self, images):
+        assert images.ndim == 5, "multiple videos per sample not supported yet"
+        video_arch = getattr(self.config, "video_arch", "temporal")
+        return video_tokens(self.get_model().get_vision_tower(), self.get_model().mm_projector, images, video_arch)
+
+    def visual_to_tokens(self, images):
+        input_type = getattr(self.config, "input_type", "image")
+        if input_type == "image":
+            return self.images_to_tokens(images)
+        elif input_type == "video":
+            return self.videos_to_tokens(images)
+
+
+def gather_hand_traj_states(hidden_states: torch.Tensor, labels: torch.Tensor, hand_token_id: int = HAND_TRAJ_TOKEN_ID,
+                            future_valid: Optional[torch.Tensor] = None, strict: bool = True):
+    """handsonvlm.py:146-187 as one kernel: returns (pred_hand_embeddings [B,2,4,D/2], valid [B] bool).
+    ``future_valid`` ([B,2] bool) is cleared in place for samples without hand tokens, like the reference.
+    strict=True reproduces the reference's failure when a sample has a hand-token count other than 0 or 4
+    (costs one 4-byte-per-sample readback); strict=False leaves the check to the caller (no host sync)."""
+    out, valid, rows, counts = ops.hand_gather(hidden_states, labels, hand_token_id)
+    if strict:
+        D = hidden_states.shape[-1]
+        for c in counts.tolist():
+            if c not in (0, 4):
+                raise RuntimeError(f"shape '[4, {D // 2}, 2]' is invalid for input of size {c * D}")
+    if future_valid is not None:
+        future_valid.logical_and_(valid.unsqueeze(-1))
+    return out, valid
+
+
+class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
+    """handsonvlm/model/handsonvlm_arch.py:8-17 + the released model's splice (handsonvlm.py:212-451)."""
+
+    def visual_to_tokens(self, images):
+        input_type = getattr(self.config, "input_type", "image")
+        if input_type == "image":
+            return self.images_to_tokens(images)
+        elif input_type == "video":
+            return self.videos_to_tokens(images)
+
+    def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images, **kwargs):
+        helper = VisualToTokenHelper(images_raw_encode=self.get_model().get_vision_tower(),
+                                     images_mm_projector=self.get_model().mm_projector,
+                                     fuse_input_mode=self.config.fuse_input_mode,
+                                     video_compress_mode=self.config.video_compress_mode,
+                                     mm_hidden_size=self.config.mm_hidden_size, token_dim=self.token_dim)
+        visual_tokens, visual_mask = helper.pipeline(images=images, **kwargs)
+        assert visual_tokens.shape == torch.Size([self.B, visual_tokens.shape[1], self.token_dim]), visual_tokens.shape
+        if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
+            raise NotImplementedError("mm_use_im_start_end splice variant is not part of the released config")
+        new_mask, embeds, new_labels = splice_tokens(
+            self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None,
+            kwargs.get("future_hands"), kwargs.get("is_evaluate", False))
+        # side effect of the reference (handsonvlm.py:288): position right after the visual block
+        is_img = input_ids[-1] == IMAGE_TOKEN_INDEX
+        self.last_visual_token_index = is_img.to(torch.int32).argmax() + visual_tokens.shape[1]
+        return None, new_mask, past_key_values, embeds, new_labels
+
+    def gather_hand_traj_states(self, hidden_states, labels, future_valid=None, strict=True):
+        return gather_hand_traj_states(hidden_states, labels, HAND_TRAJ_TOKEN_ID, future_valid, strict)

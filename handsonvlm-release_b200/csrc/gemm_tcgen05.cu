@@ -1,0 +1,417 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+ fused epilogue)
+//
+//   * A, B bf16, K-major (row-major with K contiguous) -- exactly nn.Linear's x[M,K] and weight[N,K]
+//   * TMA (cp.async.bulk.tensor, SWIZZLE_128B) fills a 4-stage shared-memory ring of [128x64] A tiles and
+//     [BNx64] B tiles; out-of-bounds rows/columns (M tail, K tail) are zero-filled by the TMA unit
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), fp32 accumulators in
+//     TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+//   * 4 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns), apply the epilogue
+//     (bias / quick-GELU / fp32 residual / ViT QKV head scatter / patch-embed + position embedding)
+//     and store 128-bit vectors
+//   * persistent: grid = min(tiles, #SM); tiles are walked N-fastest so concurrently running CTAs share
+//     A rows and the (small, L2-resident) weight matrix
+//
+// Replaces every nn.Linear on the path (see include/hvlm_b200.h).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "hvlm_internal.cuh"
+#include "hvlm_ptx.cuh"
+
+namespace hvlm {
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+        g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+    std::call_once(g_encode_once, load_encode);
+    if (!g_encode) return HVLM_ERR_CUDA;
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                          const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? HVLM_OK : HVLM_ERR_CUDA;
+}
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int check_last(const char*) { return cudaGetLastError() == cudaSuccess ? HVLM_OK : HVLM_ERR_CUDA; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 192;   // warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;   // double-buffered accumulator: 256 or 512 columns
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float quick_gelu(float x) {
+    // x * sigmoid(1.702 x)  (HF QuickGELUActivation)
+    return x / (1.0f + __expf(-1.702f * x));
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m, int n0, int M, int N,
+                                               const EpiArgs& ep) {
+    if (m >= M) return;
+    float v[32];
+    if constexpr (EPI != EPI_PATCH) {
+        if (ep.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 b = __ldg(b4 + j);
+                v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+                v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+                v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+                v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        }
+    }
+
+    if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    }
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_RESID_BF16) {
+        const float4* r4 = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(m) * N + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 r = r4[j];
+            v[4 * j + 0] += r.x;
+            v[4 * j + 1] += r.y;
+            v[4 * j + 2] += r.z;
+            v[4 * j + 3] += r.w;
+        }
+    }
+
+    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_RESID_BF16) {
+        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(m) * N + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            o[j] = w;
+        }
+    } else if constexpr (EPI == EPI_BIAS_F32 || EPI == EPI_RESID_F32 || EPI == EPI_GELU_F32) {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(m) * N + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if constexpr (EPI == EPI_QKV) {
+        // n0 in [0,3072): which = q|k|v, head, d0 in {0,32}; row m = frame*257 + tok
+        const int which = n0 >> 10;
+        const int head = (n0 & 1023) >> 6;
+        const int d0 = n0 & 63;
+        const int f = m / HVLM_VIT_TOKENS;
+        const int tok = m - f * HVLM_VIT_TOKENS;
+        const size_t fh = static_cast<size_t>(f) * HVLM_VIT_HEADS + head;
+        if (which < 2) {
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(which == 0 ? ep.q : ep.k);
+            uint4* o = reinterpret_cast<uint4*>(base + (fh * HVLM_VIT_TOKENS + tok) * 64 + d0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                o[j] = w;
+            }
+        } else {
+            // V is stored transposed ([d, key]) so that it is a K-major B operand for the P*V MMA;
+            // consecutive lanes hold consecutive tokens -> 2-byte stores coalesce across the warp.
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(ep.vt) + (fh * 64 + d0) * HVLM_VT_STRIDE + tok;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) base[static_cast<size_t>(j) * HVLM_VT_STRIDE] = __float2bfloat16_rn(v[j]);
+        }
+    } else if constexpr (EPI == EPI_PATCH) {
+        const int f = m >> 8;
+        const int p = m & 255;
+        const float4* pos4 = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(1 + p) * N + n0);
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) +
+                                              (static_cast<size_t>(f) * HVLM_VIT_TOKENS + 1 + p) * N + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 e = __ldg(pos4 + j);
+            o[j] = make_float4(__uint_as_float(acc[4 * j + 0]) + e.x, __uint_as_float(acc[4 * j + 1]) + e.y,
+                               __uint_as_float(acc[4 * j + 2]) + e.z, __uint_as_float(acc[4 * j + 3]) + e.w);
+        }
+    }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
+                    int N, int K, EpiArgs ep) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = N / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n;
+                const int n_blk = tile - m_blk * num_n;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+                    const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes (encoded >>4 => +2) per 16-element K step inside the 128-byte swizzle row
+                        umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                     idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5) =====================
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n;
+            const int n_blk = tile - m_blk * num_n;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int m = m_blk * BM + q * 32 + lane;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_row + static_cast<uint32_t>(c * 32), r);
+                tmem_ld_wait();
+                epilogue_chunk<EPI>(r, m, n_blk * BN + c * 32, M, N, ep);
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_one(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+        uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+        uint32_t box[2] = {BK, BM};
+        int rc = make_tmap_bf16(&ta, A, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+        uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+        uint32_t box[2] = {BK, BN};
+        int rc = make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    static bool attr_set[64] = {false};   // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+            return HVLM_ERR_CUDA;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * (N / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+    return check_last("gemm");
+}
+
+int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
+    if (!A || !B || M <= 0 || N <= 0 || K <= 0) return HVLM_ERR_BAD_ARG;
+    if ((N % 128) != 0 || (K % 8) != 0) return HVLM_ERR_BAD_SHAPE;
+    if (!aligned16(A) || !aligned16(B)) return HVLM_ERR_ALIGN;
+    const bool wide = (N % 256) == 0;
+#define HVLM_GEMM_CASE(E)                                                         \
+    case E:                                                                       \
+        return wide ? launch_one<256, E>(A, B, M, N, K, ep, s) : launch_one<128, E>(A, B, M, N, K, ep, s);
+    switch (epi) {
+        HVLM_GEMM_CASE(EPI_BIAS_BF16)
+        HVLM_GEMM_CASE(EPI_BIAS_F32)
+        HVLM_GEMM_CASE(EPI_GELU_BF16)
+        HVLM_GEMM_CASE(EPI_RESID_F32)
+        HVLM_GEMM_CASE(EPI_GELU_F32)
+        HVLM_GEMM_CASE(EPI_RESID_BF16)
+        case EPI_QKV:
+            return launch_one<256, EPI_QKV>(A, B, M, N, K, ep, s);
+        case EPI_PATCH:
+            return launch_one<256, EPI_PATCH>(A, B, M, N, K, ep, s);
+        default:
+            return HVLM_ERR_BAD_ARG;
+    }
+#undef HVLM_GEMM_CASE
+}
+
+}  // namespace hvlm
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int hvlm_gemm_bf16(const void* A, const void* B, const float* bias, const float* resid, void* out, int M,
+                              int N, int K, int epilogue, int out_dtype, void* stream) {
+    using namespace hvlm;
+    if (!out) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(out) || (bias && !aligned16(bias)) || (resid && !aligned16(resid))) return HVLM_ERR_ALIGN;
+    if (out_dtype != HVLM_BF16 && out_dtype != HVLM_F32) return HVLM_ERR_BAD_DTYPE;
+    EpiArgs ep;
+    ep.bias = bias;
+    ep.resid = resid;
+    ep.out = out;
+    int epi;
+    switch (epilogue) {
+        case HVLM_EPI_BIAS:
+            epi = out_dtype == HVLM_BF16 ? EPI_BIAS_BF16 : EPI_BIAS_F32;
+            break;
+        case HVLM_EPI_BIAS_QUICKGELU:
+            epi = out_dtype == HVLM_BF16 ? EPI_GELU_BF16 : EPI_GELU_F32;
+            break;
+        case HVLM_EPI_BIAS_RESIDUAL:
+            if (!resid) return HVLM_ERR_BAD_ARG;
+            epi = out_dtype == HVLM_BF16 ? EPI_RESID_BF16 : EPI_RESID_F32;
+            break;
+        default:
+            return HVLM_ERR_BAD_ARG;
+    }
+    return launch_gemm(epi, A, B, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}

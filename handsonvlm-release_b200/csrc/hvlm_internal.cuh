@@ -1,0 +1,51 @@
+// Internal (non-ABI) declarations shared by the translation units of libhvlm_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hvlm_b200.h"
+
+namespace hvlm {
+
+// ---- GEMM epilogue selectors (internal superset of hvlm_epilogue) ----------------------------------
+enum Epi : int {
+    EPI_BIAS_BF16 = 0,   // out bf16 [M,N] = acc + bias
+    EPI_BIAS_F32 = 1,    // out f32  [M,N] = acc + bias
+    EPI_GELU_BF16 = 2,   // out bf16 [M,N] = quick_gelu(acc + bias)
+    EPI_RESID_F32 = 3,   // out f32  [M,N] = resid + acc + bias (in place allowed)
+    EPI_QKV = 4,         // ViT: scatter to q / k [F,16,257,64] and v^T [F,16,64,272]
+    EPI_PATCH = 5,       // ViT: x0[f*257+1+p, n] = acc + pos[1+p, n]   (f32)
+    EPI_GELU_F32 = 6,    // out f32 = quick_gelu(acc + bias)            (tests only)
+    EPI_RESID_BF16 = 7   // out bf16 = resid + acc + bias               (tests only)
+};
+
+struct EpiArgs {
+    const float* bias = nullptr;
+    const float* resid = nullptr;
+    void* out = nullptr;
+    void* q = nullptr;
+    void* k = nullptr;
+    void* vt = nullptr;
+    const float* pos = nullptr;
+};
+
+// C = A[M,K] * B[N,K]^T with the chosen epilogue.  Returns an hvlm_status.
+int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s);
+
+// ---- TMA descriptor helper -----------------------------------------------------------------------
+// 2D/3D bf16 tensor map with SWIZZLE_128B and a [box_rows x 64] (x1) box.  dims/strides innermost first.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+int num_sms();
+int check_last(const char* what);
+
+#define HVLM_VT_STRIDE 272   // keys padded to a multiple of 8 elements (16 B) for the TMA global stride
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace hvlm

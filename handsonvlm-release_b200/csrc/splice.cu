@@ -1,0 +1,290 @@
+// Visual-token splice: index plan + index-driven row gather (forward) and gather / scatter-add (backward).
+//
+// Replaces prepare_inputs_labels_for_multimodal
+//   llava/model/llava_arch.py:110-234                                  (HVLM_SPLICE_LLAVA)
+//   handsonvlm/model/language_model/handsonvlm.py:212-451              (HVLM_SPLICE_HANDSONVLM)
+// The reference walks the batch in Python: per sample ~10 tiny kernels (embed_tokens x2, cat x3, full, where)
+// and 3 host syncs.  Here: count -> plan -> gather, three launches per batch, no host sync.  The gather fuses
+// the embed_tokens lookup, the visual rows, labels / mask construction, padding, and the sinusoidal hand
+// positional embedding (process_traj_positional_embedding, handsonvlm.py:310-338).
+#include <limits.h>
+
+#include "hvlm_internal.cuh"
+#include "hvlm_scan.cuh"
+#include "hvlm_vec.cuh"
+
+namespace hvlm {
+
+constexpr int kMaxImgPerSample = 64;
+constexpr int kPad = INT_MIN;
+
+__global__ void splice_count_kernel(const int64_t* __restrict__ ids, int T, int32_t* __restrict__ counts) {
+    __shared__ int wsum[kPlanThreads / 32];
+    const int b = blockIdx.x;
+    int c = 0;
+    for (int p = threadIdx.x; p < T; p += blockDim.x) c += (ids[static_cast<int64_t>(b) * T + p] == HVLM_IMAGE_TOKEN_INDEX);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < kPlanThreads / 32; ++w) s += wsum[w];
+        counts[b] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kPlanThreads)
+splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ counts, int B, int T, int Nv,
+                   int n_img, int L, int vocab, int variant, int hand_mode, int n_hand_points,
+                   int32_t* __restrict__ src_index, int8_t* __restrict__ hand_code, int32_t* __restrict__ lens,
+                   float* __restrict__ hand_scale, int32_t* __restrict__ status) {
+    __shared__ int scan_smem[9];
+    __shared__ int img_pos[kMaxImgPerSample];
+    const int b = blockIdx.x;
+    const int64_t* row = ids + static_cast<int64_t>(b) * T;
+    int32_t* dst = src_index + static_cast<int64_t>(b) * L;
+    int8_t* hc = hand_code + static_cast<int64_t>(b) * L;
+    int err = 0;
+
+    // image-slot base: a sample with k image tokens consumes max(k,1) slots (cur_image_idx bookkeeping)
+    int slot0 = 0;
+    for (int i = 0; i < b; ++i) slot0 += max(counts[i], 1);
+    const int k_img = counts[b];
+    const int len = T + k_img * (Nv - 1);
+    if (len > L) err |= HVLM_PLAN_ERR_LEN_OVERFLOW;
+    if (slot0 + max(k_img, 1) > n_img || k_img > kMaxImgPerSample) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
+    if (len != T + counts[0] * (Nv - 1)) err |= HVLM_PLAN_NOT_UNIFORM;
+
+    // defaults: padding + no hand code
+    for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        if (r >= len) dst[r] = kPad;
+        hc[r] = -1;
+    }
+
+    // text rows + image-token positions
+    int img_seen = 0;
+    for (int p0 = 0; p0 < T; p0 += kPlanThreads) {
+        const int p = p0 + threadIdx.x;
+        const int64_t tok = p < T ? row[p] : 0;
+        const int is_img = (p < T) && (tok == HVLM_IMAGE_TOKEN_INDEX);
+        int total;
+        const int before = img_seen + block_excl_scan(is_img, &total, scan_smem);
+        if (p < T) {
+            const int opos = p + before * (Nv - 1);
+            if (is_img) {
+                if (before < kMaxImgPerSample) img_pos[before] = p;
+            } else {
+                const bool bad = tok < 0 || tok >= vocab;   // never index the table out of bounds
+                if (bad) err |= HVLM_PLAN_ERR_BAD_ID;
+                if (opos < L) dst[opos] = bad ? kPad : p;
+            }
+        }
+        img_seen += total;
+    }
+    __syncthreads();
+
+    // visual rows
+    const int n_fill = min(k_img, kMaxImgPerSample);
+    for (int j = 0; j < n_fill; ++j) {
+        const int o0 = img_pos[j] + j * (Nv - 1);
+        const int g0 = (slot0 + j) * Nv;
+        for (int r = threadIdx.x; r < Nv; r += blockDim.x)
+            if (o0 + r < L) dst[o0 + r] = -(1 + g0 + r);
+    }
+
+    // hand positional embedding codes: only the tail segment (text after the LAST image token) of samples
+    // that have an image token (handsonvlm.py:342-396)
+    float scale = 0.f;
+    if (variant == HVLM_SPLICE_HANDSONVLM && hand_mode != 0 && k_img > 0 && k_img <= kMaxImgPerSample) {
+        const int tail0 = img_pos[k_img - 1] + 1;            // first tail position
+        const int shift = k_img * (Nv - 1);                   // output row = p + shift
+        int seen = 0;
+        for (int p0 = tail0; p0 < T; p0 += kPlanThreads) {
+            const int p = p0 + threadIdx.x;
+            const int is_hand = (p < T) && (row[p] == HVLM_HAND_TRAJ_TOKEN_ID);
+            int total;
+            const int ord = seen + block_excl_scan(is_hand, &total, scan_smem);
+            const int limit = hand_mode == 1 ? 4 : n_hand_points;
+            if (is_hand && ord < limit && p + shift < L) hc[p + shift] = static_cast<int8_t>(ord);
+            seen += total;
+        }
+        __syncthreads();
+        if (hand_mode == 1) {
+            if (seen > 4) err |= HVLM_PLAN_ERR_HAND_COUNT;
+            scale = static_cast<float>(seen) / 4.0f;
+            // zero.scatter(0, idx, emb) with idx padded by 0: row 0 of the tail receives emb[3] (last writer)
+            if (seen > 0 && seen < 4 && tail0 < T && threadIdx.x == 0 && tail0 + shift < L) hc[tail0 + shift] = 3;
+        } else {
+            if (tail0 < T && seen != n_hand_points) err |= HVLM_PLAN_ERR_HAND_COUNT;
+            scale = 1.0f;
+        }
+    }
+    if (threadIdx.x == 0) {
+        lens[b] = len;
+        if (hand_scale) hand_scale[b] = scale;
+    }
+    if (err) atomicOr(status, err);
+}
+
+// sinusoidal hand embedding value for output channel `ch` (handsonvlm.py:310-338):
+//   out[k, 2c+h] = enc(hand h, point k)[c],  enc = cat[sin(x f), cos(y f), sin(x f), cos(y f)],
+//   f_i = 10000^(-2i/(D/4)), i in [0, D/8)
+__device__ __forceinline__ float hand_embed_value(const float* __restrict__ fh /*[2,n,2] of sample*/, int n, int k,
+                                                  int ch, int D) {
+    const int h = ch & 1;
+    const int c = ch >> 1;
+    const int eighth = D >> 3;
+    const int seg = c / eighth;
+    const int i = c - seg * eighth;
+    const float freq = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / static_cast<float>(D >> 2));
+    const float* pt = fh + (h * n + k) * 2;
+    return (seg & 1) ? cosf(pt[1] * freq) : sinf(pt[0] * freq);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+splice_fwd_kernel(const int32_t* __restrict__ src_index, const int8_t* __restrict__ hand_code,
+                  const int32_t* __restrict__ lens, const float* __restrict__ hand_scale,
+                  const int64_t* __restrict__ ids, const int64_t* __restrict__ labels,
+                  const uint8_t* __restrict__ mask, const T* __restrict__ table, const T* __restrict__ visual,
+                  const uint8_t* __restrict__ visual_mask, const float* __restrict__ future_hands, int n_hand, int Tlen,
+                  int L, int Nv, int D, int variant, T* __restrict__ out, int64_t* __restrict__ out_labels,
+                  uint8_t* __restrict__ out_mask) {
+    constexpr int V = Vec16<T>::N;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int64_t orow = static_cast<int64_t>(b) * L + r;
+    const int code = src_index[orow];
+    const int hk = hand_code ? hand_code[orow] : -1;
+    const T* src = nullptr;
+    int64_t lab = HVLM_IGNORE_INDEX;
+    uint8_t mk = 0;
+    if (code >= 0) {
+        const int64_t ipos = static_cast<int64_t>(b) * Tlen + code;
+        src = table + ids[ipos] * D;
+        if (labels) lab = labels[ipos];
+        if (mask) mk = mask[ipos];
+    } else if (code != kPad) {
+        const int g = -(code + 1);
+        src = visual + static_cast<int64_t>(g) * D;
+        mk = visual_mask ? visual_mask[g] : 1;
+    }
+    if (threadIdx.x == 0) {
+        if (out_labels) out_labels[orow] = lab;
+        if (out_mask) {
+            if (variant == HVLM_SPLICE_LLAVA && mask) {
+                // llava_arch.py:215-232: True x (len - T) prepended, original mask, False right-pad
+                const int len = lens[b];
+                const int lead = len - Tlen;
+                mk = r < lead ? 1 : (r < len ? mask[static_cast<int64_t>(b) * Tlen + (r - lead)] : 0);
+            }
+            out_mask[orow] = mk;
+        }
+    }
+    T* dst = out + orow * D;
+    const float hs = (hk >= 0 && hand_scale) ? hand_scale[b] : 0.f;
+    const float* fh = (hk >= 0 && future_hands) ? future_hands + static_cast<int64_t>(b) * 2 * n_hand * 2 : nullptr;
+    for (int c = threadIdx.x * V; c < D; c += blockDim.x * V) {
+        uint4 raw = src ? *reinterpret_cast<const uint4*>(src + c) : make_uint4(0, 0, 0, 0);
+        if (fh) {
+            float f[V];
+            unpack16<T>(raw, f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) f[i] += hs * hand_embed_value(fh, n_hand, hk, c + i, D);
+            raw = pack16<T>(f);
+        }
+        *reinterpret_cast<uint4*>(dst + c) = raw;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+splice_bwd_kernel(const T* __restrict__ d_embeds, const int32_t* __restrict__ src_index,
+                  const int64_t* __restrict__ ids, int Tlen, int L, int n_visual_rows, int D,
+                  float* __restrict__ d_visual, float* __restrict__ d_table) {
+    constexpr int V = Vec16<T>::N;
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int64_t orow = static_cast<int64_t>(b) * L + r;
+    const int code = src_index[orow];
+    if (code == kPad) return;
+    const T* src = d_embeds + orow * D;
+    if (code >= 0) {
+        if (!d_table) return;
+        float* dst = d_table + ids[static_cast<int64_t>(b) * Tlen + code] * D;
+        for (int c = threadIdx.x * V; c < D; c += blockDim.x * V) {
+            float f[V];
+            unpack16<T>(*reinterpret_cast<const uint4*>(src + c), f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) atomicAdd(dst + c + i, f[i]);
+        }
+    } else {
+        const int g = -(code + 1);
+        if (!d_visual || g >= n_visual_rows) return;
+        float* dst = d_visual + static_cast<int64_t>(g) * D;
+        for (int c = threadIdx.x * V; c < D; c += blockDim.x * V) {
+            float f[V];
+            unpack16<T>(*reinterpret_cast<const uint4*>(src + c), f);
+#pragma unroll
+            for (int i = 0; i < V; ++i) dst[c + i] = f[i];
+        }
+    }
+}
+
+}  // namespace hvlm
+
+extern "C" int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* counts, void* stream) {
+    using namespace hvlm;
+    if (!ids || !counts || B <= 0 || T <= 0) return HVLM_ERR_BAD_ARG;
+    splice_count_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(ids, T, counts);
+    return check_last("splice_count");
+}
+
+extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B, int T, int Nv, int n_img, int L,
+                                int vocab, int variant, int hand_mode, int n_hand_points, int32_t* src_index,
+                                int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status, void* stream) {
+    using namespace hvlm;
+    if (!ids || !counts || !src_index || !hand_code || !lens || !status) return HVLM_ERR_BAD_ARG;
+    if (B <= 0 || T <= 0 || Nv <= 0 || n_img <= 0 || L <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
+    if (variant != HVLM_SPLICE_LLAVA && variant != HVLM_SPLICE_HANDSONVLM) return HVLM_ERR_BAD_ARG;
+    if (hand_mode < 0 || hand_mode > 2 || n_hand_points < 0 || n_hand_points > 127) return HVLM_ERR_BAD_ARG;
+    splice_plan_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, counts, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index, hand_code, lens,
+        hand_scale, status);
+    return check_last("splice_plan");
+}
+
+extern "C" int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens,
+                               const float* hand_scale, const int64_t* ids, const int64_t* labels,
+                               const uint8_t* mask, const void* embed_table, const void* visual,
+                               const uint8_t* visual_mask, const float* future_hands, int n_hand_points, int B, int T,
+                               int L, int Nv, int D, int dtype, int variant, void* out_embeds, int64_t* out_labels,
+                               uint8_t* out_mask, void* stream) {
+    using namespace hvlm;
+    if (!src_index || !lens || !ids || !embed_table || !visual || !out_embeds) return HVLM_ERR_BAD_ARG;
+    if (B <= 0 || T <= 0 || L <= 0 || Nv <= 0 || D <= 0) return HVLM_ERR_BAD_ARG;
+    if (future_hands && (!hand_code || !hand_scale || n_hand_points <= 0)) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(embed_table) || !aligned16(visual) || !aligned16(out_embeds)) return HVLM_ERR_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HVLM_DISPATCH_DTYPE(dtype, TT, {
+        if (D % Vec16<TT>::N != 0 || (future_hands && (D % 8) != 0)) return HVLM_ERR_BAD_SHAPE;
+        splice_fwd_kernel<TT><<<dim3(L, B), 128, 0, s>>>(
+            src_index, hand_code, lens, hand_scale, ids, labels, mask, static_cast<const TT*>(embed_table),
+            static_cast<const TT*>(visual), visual_mask, future_hands, n_hand_points, T, L, Nv, D, variant,
+            static_cast<TT*>(out_embeds), out_labels, out_mask);
+    });
+    return check_last("splice_fwd");
+}
+
+extern "C" int hvlm_splice_bwd(const void* d_embeds, int dtype, const int32_t* src_index, const int64_t* ids, int B,
+                               int T, int L, int n_visual_rows, int D, float* d_visual, float* d_embed_table,
+                               void* stream) {
+    using namespace hvlm;
+    if (!d_embeds || !src_index || !ids || B <= 0 || T <= 0 || L <= 0 || D <= 0) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(d_embeds)) return HVLM_ERR_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HVLM_DISPATCH_DTYPE(dtype, TT, {
+        if (D % Vec16<TT>::N != 0) return HVLM_ERR_BAD_SHAPE;
+        splice_bwd_kernel<TT><<<dim3(L, B), 128, 0, s>>>(static_cast<const TT*>(d_embeds), src_index, ids, T, L,
+                                                        n_visual_rows, D, d_visual, d_embed_table);
+    });
+    return check_last("splice_bwd");
+}

@@ -1,0 +1,478 @@
+"""PyTorch custom ops over the C ABI (include/hvlm_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current CUDA stream; every op hands raw
+pointers to libhvlm_b200.so.  Ops are registered with ``torch.library`` (namespace ``hvlm``) with fake
+(meta) kernels for shape propagation and autograd formulas for the training-shaped variant
+(pooling, projector, splice, gather).  There is no CPU implementation: calling an op with a
+non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hvlm ops run on sm_100a CUDA devices only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}") from None
+
+
+_checked = set()
+
+
+def ensure_device(index: Optional[int] = None) -> None:
+    """Fail loudly unless the current device is an sm_100 GPU and the extension is loaded."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("hvlm_b200 needs an sm_100a (B200) GPU; no CUDA device is visible")
+    index = torch.cuda.current_device() if index is None else index
+    if index not in _checked:
+        L.check(L.lib().hvlm_device_check(index), "hvlm_device_check")
+        _checked.add(index)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM (nn.Linear):  y = x @ w.T (+ b) with fused epilogue
+# ------------------------------------------------------------------------------------------------
+def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: str = "bias",
+         resid: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [M,K] bf16, w [N,K] bf16, bias [N] f32, resid [M,N] f32 -> [M,N]."""
+    _need_cuda(x, w, bias, resid)
+    ensure_device()
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "operands must be bf16"
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1]
+    x, w = x.contiguous(), w.contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+        bias = bias.contiguous()
+    epi = {"bias": L.EPI_BIAS, "quick_gelu": L.EPI_BIAS_QUICKGELU, "residual": L.EPI_BIAS_RESIDUAL}[epilogue]
+    if epi == L.EPI_BIAS_RESIDUAL:
+        assert resid is not None and resid.dtype == torch.float32 and tuple(resid.shape) == (M, N)
+        resid = resid.contiguous()
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    L.check(L.lib().hvlm_gemm_bf16(_p(x), _p(w), _p(bias), _p(resid), _p(out), M, N, K, epi, _DT[out.dtype], _stream()),
+            "hvlm_gemm_bf16")
+    return out
+
+
+def transpose_to_bf16(x: torch.Tensor, r_pad: Optional[int] = None) -> torch.Tensor:
+    """x [R,C] -> bf16 [C, R_pad] (zero padded; R_pad multiple of 8)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    R, Cc = x.shape
+    r_pad = (R + 7) // 8 * 8 if r_pad is None else r_pad
+    out = torch.empty(Cc, r_pad, dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().hvlm_transpose_to_bf16(_p(x), _dt(x), _p(out), R, Cc, r_pad, _stream()), "hvlm_transpose_to_bf16")
+    return out
+
+
+def colsum(dy: torch.Tensor) -> torch.Tensor:
+    _need_cuda(dy)
+    dy = dy.contiguous()
+    M, N = dy.shape
+    out = torch.empty(N, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().hvlm_colsum(_p(dy), _dt(dy), _p(out), M, N, _stream()), "hvlm_colsum")
+    return out
+
+
+@torch.library.custom_op("hvlm::linear", mutates_args=())
+def linear(x: torch.Tensor, w_bf16: torch.Tensor, bias_f32: torch.Tensor, out_f32: bool) -> torch.Tensor:
+    """mm_projector forward: x [M,K] (any float dtype, rounded to bf16), w [N,K] bf16, bias [N] f32."""
+    xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    return gemm(xb, w_bf16, bias_f32, epilogue="bias", out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+
+
+@linear.register_fake
+def _(x, w_bf16, bias_f32, out_f32):
+    return x.new_empty(x.shape[0], w_bf16.shape[0], dtype=torch.float32 if out_f32 else torch.bfloat16)
+
+
+@torch.library.custom_op("hvlm::linear_bwd", mutates_args=())
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w_bf16: torch.Tensor, need_dx: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """dW [N,K] f32 = dY^T X, db [N] f32 = colsum(dY), dX [M,K] f32 = dY W (only if need_dx)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dyT = transpose_to_bf16(dy)                  # [N, Mp]   A operand, K-major over tokens
+    xT = transpose_to_bf16(x)                    # [K, Mp]   B operand
+    dW = gemm(dyT, xT, None, out_dtype=torch.float32)
+    db = colsum(dy)
+    if need_dx:
+        wT = transpose_to_bf16(w_bf16)           # [K, N]
+        dyb = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
+        dx = gemm(dyb.contiguous(), wT, None, out_dtype=torch.float32)
+    else:
+        dx = torch.empty(0, dtype=torch.float32, device=dy.device)
+    return dW, db, dx
+
+
+@linear_bwd.register_fake
+def _(dy, x, w_bf16, need_dx):
+    N, K = w_bf16.shape
+    return (dy.new_empty(N, K, dtype=torch.float32), dy.new_empty(N, dtype=torch.float32),
+            dy.new_empty((x.shape[0], K) if need_dx else (0,), dtype=torch.float32))
+
+
+def _linear_setup(ctx, inputs, output):
+    x, w, b, _ = inputs
+    ctx.save_for_backward(x, w)
+    ctx.need_dx = x.requires_grad
+
+
+def _linear_backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    dW, db, dx = linear_bwd(dy.contiguous(), x, w, ctx.need_dx)
+    return (dx.to(x.dtype) if ctx.need_dx else None), dW.to(w.dtype), db, None
+
+
+linear.register_autograd(_linear_backward, setup_context=_linear_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# ViT-L/14 tower
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("hvlm::vit_l14_hidden", mutates_args=())
+def vit_l14_hidden(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run: int) -> torch.Tensor:
+    """pixels [N,3,224,224] -> residual stream f32 [N,257,1024] after n_layers_run layers."""
+    _need_cuda(weight_blob, pixels)
+    ensure_device()
+    if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, 224, 224):
+        raise ValueError(f"Input image size ({tuple(pixels.shape[-2:])}) doesn't match model (224*224).")
+    pixels = pixels.contiguous()
+    N = pixels.shape[0]
+    lib = L.lib()
+    ws_bytes = lib.hvlm_vit_l14_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
+    hidden = torch.empty(N, 257, 1024, dtype=torch.float32, device=pixels.device)
+    L.check(lib.hvlm_vit_l14_fwd(_p(weight_blob), n_layers_run, _p(pixels), _dt(pixels), N, _p(hidden), _p(ws),
+                                 ws_bytes, _stream()), "hvlm_vit_l14_fwd")
+    return hidden
+
+
+@vit_l14_hidden.register_fake
+def _(weight_blob, pixels, n_layers_run):
+    return pixels.new_empty(pixels.shape[0], 257, 1024, dtype=torch.float32)
+
+
+def feature_select(hidden: torch.Tensor, out_dtype: torch.dtype, keep_cls: bool = False) -> torch.Tensor:
+    _need_cuda(hidden)
+    N = hidden.shape[0]
+    out = torch.empty(N, 257 if keep_cls else 256, 1024, dtype=out_dtype, device=hidden.device)
+    L.check(L.lib().hvlm_feature_select(_p(hidden), _p(out), N, _DT[out_dtype], int(keep_cls), _stream()),
+            "hvlm_feature_select")
+    return out
+
+
+def layernorm_1024(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, out_dtype=torch.bfloat16, eps=1e-5):
+    _need_cuda(x, g, b)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    L.check(L.lib().hvlm_layernorm_1024(_p(x), _p(g), _p(b), _p(out), x.numel() // 1024, _DT[out_dtype], eps, _stream()),
+            "hvlm_layernorm_1024")
+    return out
+
+
+def vit_qkv(y: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, n_frames: int):
+    _need_cuda(y, w_qkv, b_qkv)
+    dev = y.device
+    q = torch.empty(n_frames, 16, 257, 64, dtype=torch.bfloat16, device=dev)
+    k = torch.empty_like(q)
+    vt = torch.zeros(n_frames, 16, 64, 272, dtype=torch.bfloat16, device=dev)
+    L.check(L.lib().hvlm_vit_qkv_gemm(_p(y), _p(w_qkv), _p(b_qkv), _p(q), _p(k), _p(vt), n_frames, _stream()),
+            "hvlm_vit_qkv_gemm")
+    return q, k, vt
+
+
+def vit_attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor) -> torch.Tensor:
+    _need_cuda(q, k, vt)
+    n_frames = q.shape[0]
+    out = torch.empty(n_frames * 257, 1024, dtype=torch.bfloat16, device=q.device)
+    L.check(L.lib().hvlm_vit_attention(_p(q), _p(k), _p(vt), _p(out), n_frames, _stream()), "hvlm_vit_attention")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# slow-fast pooling
+# ------------------------------------------------------------------------------------------------
+def pool_out_tokens(t: int, mode: str) -> int:
+    return L.lib().hvlm_pool_out_tokens(t, L.POOL_MODES[mode])
+
+
+@torch.library.custom_op("hvlm::pool_slowfast", mutates_args=())
+def pool_slowfast(tok: torch.Tensor, B: int, t: int, frame_stride: int, row_offset: int, mode: int,
+                  out_bf16: bool) -> torch.Tensor:
+    """tok: flat buffer viewed as [B*t, frame_stride, C] (rows row_offset..row_offset+255 of each frame are the
+    256 tokens) -> [B, n_out, C].  frame_stride=257,row_offset=1 reads the tower's hidden state in place."""
+    _need_cuda(tok)
+    ensure_device()
+    assert tok.is_contiguous() and tok.dim() == 3 and tok.shape[0] == B * t and tok.shape[1] == frame_stride
+    assert row_offset + 256 <= frame_stride
+    Cc = tok.shape[2]
+    lib = L.lib()
+    n_out = lib.hvlm_pool_out_tokens(t, mode)
+    out = torch.empty(B, n_out, Cc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=tok.device)
+    base = C.c_void_p(tok.data_ptr() + row_offset * Cc * tok.element_size())
+    L.check(lib.hvlm_pool_slowfast_fwd(base, _dt(tok), frame_stride, _p(out), _DT[out.dtype], B, t, Cc, mode, _stream()),
+            "hvlm_pool_slowfast_fwd")
+    return out
+
+
+@pool_slowfast.register_fake
+def _(tok, B, t, frame_stride, row_offset, mode, out_bf16):
+    n_out = {0: t + 256, 1: 256, 2: t, 3: 256, 4: t + 256}[mode]
+    return tok.new_empty(B, n_out, tok.shape[2], dtype=torch.bfloat16 if out_bf16 else torch.float32)
+
+
+@torch.library.custom_op("hvlm::pool_slowfast_bwd", mutates_args=())
+def pool_slowfast_bwd(dout: torch.Tensor, t: int, mode: int, out_bf16: bool) -> torch.Tensor:
+    _need_cuda(dout)
+    dout = dout.contiguous()
+    B, _, Cc = dout.shape
+    dtok = torch.empty(B, t, 256, Cc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dout.device)
+    L.check(L.lib().hvlm_pool_slowfast_bwd(_p(dout), _dt(dout), _p(dtok), _DT[dtok.dtype], B, t, Cc, mode, _stream()),
+            "hvlm_pool_slowfast_bwd")
+    return dtok
+
+
+@pool_slowfast_bwd.register_fake
+def _(dout, t, mode, out_bf16):
+    return dout.new_empty(dout.shape[0], t, 256, dout.shape[2], dtype=torch.bfloat16 if out_bf16 else torch.float32)
+
+
+def _pool_setup(ctx, inputs, output):
+    tok, B, t, frame_stride, row_offset, mode, _ = inputs
+    ctx.t, ctx.mode, ctx.frame_stride, ctx.row_offset, ctx.in_dtype, ctx.B = t, mode, frame_stride, row_offset, tok.dtype, B
+
+
+def _pool_backward(ctx, dout):
+    d = pool_slowfast_bwd(dout.contiguous(), ctx.t, ctx.mode, ctx.in_dtype == torch.bfloat16)
+    d = d.reshape(ctx.B * ctx.t, 256, -1)
+    if ctx.frame_stride != 256:
+        full = d.new_zeros(ctx.B * ctx.t, ctx.frame_stride, d.shape[-1])
+        full[:, ctx.row_offset:ctx.row_offset + 256] = d
+        d = full
+    return d.to(ctx.in_dtype), None, None, None, None, None, None
+
+
+pool_slowfast.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+def pool_tokens(tokens: torch.Tensor, mode: str, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """tokens [b,t,256,C] -> [b,n_out,C]  (compress_tokens / videos_to_tokens pooling)."""
+    b, t, s, c = tokens.shape
+    assert s == 256, f"tokens.shape = {tuple(tokens.shape)}"
+    out_dtype = tokens.dtype if out_dtype is None else out_dtype
+    return pool_slowfast(tokens.contiguous().reshape(b * t, 256, c), b, t, 256, 0, L.POOL_MODES[mode],
+                         out_dtype == torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+# splice
+# ------------------------------------------------------------------------------------------------
+def splice_count(ids: torch.Tensor) -> torch.Tensor:
+    _need_cuda(ids)
+    ensure_device()
+    ids = ids.contiguous()
+    B, T = ids.shape
+    counts = torch.empty(B, dtype=torch.int32, device=ids.device)
+    L.check(L.lib().hvlm_splice_count(_p(ids), B, T, _p(counts), _stream()), "hvlm_splice_count")
+    return counts
+
+
+def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lout: int, vocab: int, variant: int,
+                hand_mode: int, n_hand: int):
+    ids = ids.contiguous()
+    B, T = ids.shape
+    dev = ids.device
+    src_index = torch.empty(B, Lout, dtype=torch.int32, device=dev)
+    hand_code = torch.empty(B, Lout, dtype=torch.int8, device=dev)
+    lens = torch.empty(B, dtype=torch.int32, device=dev)
+    hand_scale = torch.empty(B, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(L.lib().hvlm_splice_plan(_p(ids), _p(counts), B, T, Nv, n_img, Lout, vocab, variant, hand_mode, n_hand,
+                                     _p(src_index), _p(hand_code), _p(lens), _p(hand_scale), _p(status), _stream()),
+            "hvlm_splice_plan")
+    return src_index, hand_code, lens, hand_scale, status
+
+
+@torch.library.custom_op("hvlm::splice_gather", mutates_args=())
+def splice_gather(src_index: torch.Tensor, hand_code: torch.Tensor, lens: torch.Tensor, hand_scale: torch.Tensor,
+                  ids: torch.Tensor, labels: Optional[torch.Tensor], mask: Optional[torch.Tensor],
+                  table: torch.Tensor, visual: torch.Tensor, visual_mask: Optional[torch.Tensor],
+                  future_hands: Optional[torch.Tensor], variant: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Index-driven gather -> (embeds [B,L,D], labels [B,L] i64, mask [B,L] bool)."""
+    _need_cuda(src_index, ids, table, visual)
+    B, Lout = src_index.shape
+    T = ids.shape[1]
+    n_img, Nv, D = visual.shape
+    assert table.dtype == visual.dtype, (table.dtype, visual.dtype)
+    dev = ids.device
+    embeds = torch.empty(B, Lout, D, dtype=table.dtype, device=dev)
+    out_labels = torch.empty(B, Lout, dtype=torch.int64, device=dev)
+    out_mask = torch.empty(B, Lout, dtype=torch.bool, device=dev)
+    n_hand = 0
+    if future_hands is not None:
+        future_hands = future_hands.to(torch.float32).contiguous()
+        n_hand = future_hands.shape[2]
+    mask_u8 = None if mask is None else mask.contiguous().view(torch.uint8)
+    vmask_u8 = None if visual_mask is None else visual_mask.contiguous().view(torch.uint8)
+    L.check(L.lib().hvlm_splice_fwd(_p(src_index), _p(hand_code), _p(lens), _p(hand_scale), _p(ids.contiguous()),
+                                    _p(None if labels is None else labels.contiguous()), _p(mask_u8),
+                                    _p(table.contiguous()), _p(visual.contiguous()), _p(vmask_u8), _p(future_hands),
+                                    n_hand, B, T, Lout, Nv, D, _dt(table), variant, _p(embeds), _p(out_labels),
+                                    _p(out_mask.view(torch.uint8)), _stream()), "hvlm_splice_fwd")
+    return embeds, out_labels, out_mask
+
+
+@splice_gather.register_fake
+def _(src_index, hand_code, lens, hand_scale, ids, labels, mask, table, visual, visual_mask, future_hands, variant):
+    B, Lout = src_index.shape
+    return (table.new_empty(B, Lout, table.shape[1]), ids.new_empty(B, Lout), ids.new_empty(B, Lout, dtype=torch.bool))
+
+
+@torch.library.custom_op("hvlm::splice_bwd", mutates_args=())
+def splice_bwd(d_embeds: torch.Tensor, src_index: torch.Tensor, ids: torch.Tensor, n_visual_rows: int, vocab: int,
+               need_table: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda(d_embeds)
+    d_embeds = d_embeds.contiguous()
+    B, Lout, D = d_embeds.shape
+    dev = d_embeds.device
+    # visual rows that no sample references keep a zero gradient
+    d_visual = torch.zeros(n_visual_rows, D, dtype=torch.float32, device=dev)
+    d_table = torch.zeros(vocab, D, dtype=torch.float32, device=dev) if need_table else torch.empty(0, device=dev)
+    L.check(L.lib().hvlm_splice_bwd(_p(d_embeds), _dt(d_embeds), _p(src_index), _p(ids.contiguous()), B, ids.shape[1],
+                                    Lout, n_visual_rows, D, _p(d_visual), _p(d_table if need_table else None),
+                                    _stream()), "hvlm_splice_bwd")
+    return d_visual, d_table
+
+
+@splice_bwd.register_fake
+def _(d_embeds, src_index, ids, n_visual_rows, vocab, need_table):
+    D = d_embeds.shape[2]
+    return (d_embeds.new_empty(n_visual_rows, D, dtype=torch.float32),
+            d_embeds.new_empty((vocab, D) if need_table else (0,), dtype=torch.float32))
+
+
+def _splice_setup(ctx, inputs, output):
+    src_index, _, _, _, ids, _, _, table, visual, _, _, _ = inputs
+    ctx.save_for_backward(src_index, ids)
+    ctx.vshape = visual.shape
+    ctx.vocab = table.shape[0]
+    ctx.need_table = table.requires_grad
+    ctx.need_visual = visual.requires_grad
+    ctx.tdtype, ctx.vdtype = table.dtype, visual.dtype
+    ctx.set_materialize_grads(False)
+
+
+def _splice_backward(ctx, d_embeds, d_labels, d_mask):
+    src_index, ids = ctx.saved_tensors
+    gv = gt = None
+    if d_embeds is not None and (ctx.need_table or ctx.need_visual):
+        n_img, Nv, D = ctx.vshape
+        d_visual, d_table = splice_bwd(d_embeds, src_index, ids, n_img * Nv, ctx.vocab, ctx.need_table)
+        if ctx.need_visual:
+            gv = d_visual.reshape(n_img, Nv, D).to(ctx.vdtype)
+        if ctx.need_table:
+            gt = d_table.to(ctx.tdtype)
+    return None, None, None, None, None, None, None, gt, gv, None, None, None
+
+
+splice_gather.register_autograd(_splice_backward, setup_context=_splice_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# <hand_traj> gather
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("hvlm::hand_gather", mutates_args=())
+def hand_gather(hidden: torch.Tensor, labels: torch.Tensor, hand_id: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (out [B,2,4,D/2], valid [B] bool, rows [B,4] i32, counts [B] i32)."""
+    _need_cuda(hidden, labels)
+    ensure_device()
+    hidden, labels = hidden.contiguous(), labels.contiguous()
+    B, Lh, D = hidden.shape
+    dev = hidden.device
+    out = torch.empty(B, 2, 4, D // 2, dtype=hidden.dtype, device=dev)
+    valid = torch.empty(B, dtype=torch.bool, device=dev)
+    rows = torch.empty(B, 4, dtype=torch.int32, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    L.check(L.lib().hvlm_hand_gather_fwd(_p(hidden), _dt(hidden), _p(labels), hand_id, B, Lh, D, _p(out),
+                                         _p(valid.view(torch.uint8)), _p(rows), _p(counts), _stream()),
+            "hvlm_hand_gather_fwd")
+    return out, valid, rows, counts
+
+
+@hand_gather.register_fake
+def _(hidden, labels, hand_id):
+    B, Lh, D = hidden.shape
+    return (hidden.new_empty(B, 2, 4, D // 2), hidden.new_empty(B, dtype=torch.bool),
+            hidden.new_empty(B, 4, dtype=torch.int32), hidden.new_empty(B, dtype=torch.int32))
+
+
+@torch.library.custom_op("hvlm::hand_gather_bwd", mutates_args=())
+def hand_gather_bwd(dout: torch.Tensor, rows: torch.Tensor, Lh: int) -> torch.Tensor:
+    _need_cuda(dout, rows)
+    dout = dout.contiguous()
+    B, _, _, half = dout.shape
+    dh = torch.zeros(B, Lh, 2 * half, dtype=torch.float32, device=dout.device)
+    L.check(L.lib().hvlm_hand_gather_bwd(_p(dout), _dt(dout), _p(rows), B, Lh, 2 * half, _p(dh), _stream()),
+            "hvlm_hand_gather_bwd")
+    return dh
+
+
+@hand_gather_bwd.register_fake
+def _(dout, rows, Lh):
+    return dout.new_empty(dout.shape[0], Lh, 2 * dout.shape[3], dtype=torch.float32)
+
+
+def _gather_setup(ctx, inputs, output):
+    hidden, _, _ = inputs
+    ctx.save_for_backward(output[2])
+    ctx.Lh, ctx.dtype = hidden.shape[1], hidden.dtype
+    ctx.set_materialize_grads(False)
+
+
+def _gather_backward(ctx, dout, dvalid, drows, dcounts):
+    if dout is None:
+        return None, None, None
+    (rows,) = ctx.saved_tensors
+    return hand_gather_bwd(dout, rows, ctx.Lh).to(ctx.dtype), None, None
+
+
+hand_gather.register_autograd(_gather_backward, setup_context=_gather_setup)
+
+
+def hand_gather_step(hidden_last: torch.Tensor) -> torch.Tensor:
+    """Generation-time gather (handsonvlm.py:613-616): [B,D] -> [B,2,1,D/2]."""
+    _need_cuda(hidden_last)
+    ensure_device()
+    hidden_last = hidden_last.contiguous()
+    B, D = hidden_last.shape
+    out = torch.empty(B, 2, 1, D // 2, dtype=hidden_last.dtype, device=hidden_last.device)
+    L.check(L.lib().hvlm_hand_gather_step(_p(hidden_last), _dt(hidden_last), B, D, _p(out), _stream()),
+            "hvlm_hand_gather_step")
+    return out

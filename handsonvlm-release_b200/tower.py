@@ -1,0 +1,110 @@
+"""Drop-in for the reference's CLIP vision tower wrapper.
+
+Mirrors ``CLIPVisionTower`` (llava/model/multimodal_encoder/clip_encoder.py:7-78): same constructor arguments,
+``forward(images)`` (tensor or list), ``feature_select`` semantics (``select_layer``, ``select_feature`` in
+{'patch','cls_patch'}), and the ``dummy_feature / dtype / device / config / hidden_size / num_patches`` properties.
+The HF ``CLIPVisionModel`` underneath is replaced by the sm_100a kernels behind ``hvlm_vit_l14_fwd``.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .weights import pack_vit_weights
+
+_CFG = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16, image_size=224,
+            patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5, projection_dim=768)
+
+
+class CLIPVisionTower(nn.Module):
+    def __init__(self, vision_tower="openai/clip-vit-large-patch14", args=None, delay_load=False):
+        super().__init__()
+        self.is_loaded = False
+        self.vision_tower_name = vision_tower
+        self.select_layer = getattr(args, "mm_vision_select_layer", -2)
+        self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
+        self.cfg_only = types.SimpleNamespace(**_CFG)
+        self._dtype = torch.bfloat16
+        self.register_buffer("weight_blob", torch.zeros(0, dtype=torch.uint8), persistent=False)
+        if not delay_load and isinstance(vision_tower, dict):
+            self.load_model(vision_tower)
+
+    # -- loading -------------------------------------------------------------------------------
+    def load_model(self, state_dict=None):
+        """``state_dict``: HF-named CLIPVisionModel tensors.  (The reference calls ``from_pretrained`` here;
+        there is no network in this environment, so the weights are handed in; a path to a ``.pt``/``.bin``
+        state dict is also accepted.)"""
+        if state_dict is None:
+            state_dict = self.vision_tower_name
+        if isinstance(state_dict, str):
+            state_dict = torch.load(state_dict, map_location="cpu")
+        dev = self.weight_blob.device
+        blob = pack_vit_weights(state_dict, n_layers=self.n_layers_needed)
+        self._blob_layers = blob.hvlm_n_layers
+        if self._blob_layers < self.n_layers_needed:
+            raise ValueError(f"state dict has {self._blob_layers} encoder layers, select_layer={self.select_layer} "
+                             f"needs {self.n_layers_needed}")
+        self.weight_blob = blob.to(dev)
+        self.requires_grad_(False)
+        self.is_loaded = True
+
+    @property
+    def n_layers_needed(self) -> int:
+        L = _CFG["num_hidden_layers"]
+        return self.select_layer if self.select_layer >= 0 else L + 1 + self.select_layer
+
+    # -- forward -------------------------------------------------------------------------------
+    def feature_select(self, hidden: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+        if self.select_feature == "patch":
+            return ops.feature_select(hidden, out_dtype, keep_cls=False)
+        elif self.select_feature == "cls_patch":
+            return ops.feature_select(hidden, out_dtype, keep_cls=True)
+        raise ValueError(f"Unexpected select feature: {self.select_feature}")
+
+    def forward_hidden(self, images: torch.Tensor) -> torch.Tensor:
+        """fp32 residual stream [N,257,1024] == HF hidden_states[select_layer] (no copy of the patch rows)."""
+        if not self.is_loaded:
+            raise RuntimeError("CLIPVisionTower.load_model() has not been called")
+        if images.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            images = images.float()
+        return ops.vit_l14_hidden(self.weight_blob, images.to(self.device), self.n_layers_needed)
+
+    @torch.no_grad()
+    def forward(self, images):
+        if type(images) is list:
+            image_features = []
+            for image in images:
+                hidden = self.forward_hidden(image.unsqueeze(0))
+                image_features.append(self.feature_select(hidden, image.dtype))
+        else:
+            hidden = self.forward_hidden(images)
+            image_features = self.feature_select(hidden, images.dtype)
+        return image_features
+
+    # -- properties ----------------------------------------------------------------------------
+    @property
+    def dummy_feature(self):
+        return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        return self.weight_blob.device
+
+    @property
+    def config(self):
+        return self.cfg_only
+
+    @property
+    def hidden_size(self):
+        return self.config.hidden_size
+
+    @property
+    def num_patches(self):
+        return (self.config.image_size // self.config.patch_size) ** 2

@@ -1,0 +1,240 @@
+/*
+ * hvlm_b200.h -- C ABI of the B200-native (sm_100a) HandsOnVLM visual-token path.
+ *
+ * The reference (Kami-code/HandsOnVLM-release) has NO native / FFI boundary: the path is five Python
+ * methods.  This header is the boundary a maintainer would bind instead; every entry
+ * point names the reference code it replaces (paths relative to the reference checkout).  The Python
+ * drop-ins in handsonvlm-release_b200/ call exactly these symbols through ctypes, wrapped as
+ * torch.library custom ops (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the caller owns all buffers (inputs, outputs, workspace); nothing is retained after return
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the host
+ *   - return value: 0 (HVLM_OK) or a negative hvlm_status; never throws, never aborts
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry returns HVLM_ERR_CUDA
+ *   - "bf16 GEMM regime": bf16 operands, fp32 accumulation in TMEM (tcgen05.mma kind::f16)
+ */
+#ifndef HVLM_B200_H
+#define HVLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVLM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HVLM_API __attribute__((visibility("default")))
+#else
+#define HVLM_API
+#endif
+
+typedef enum {
+    HVLM_OK = 0,
+    HVLM_ERR_BAD_ARG = -1,      /* null pointer / negative size / unknown enum */
+    HVLM_ERR_BAD_SHAPE = -2,    /* shape the kernels do not support (e.g. tokens/frame != 256) */
+    HVLM_ERR_BAD_DTYPE = -3,
+    HVLM_ERR_ALIGN = -4,        /* pointer not 16-byte aligned */
+    HVLM_ERR_CUDA = -5,         /* launch / driver failure, or no sm_100 device */
+    HVLM_ERR_WORKSPACE = -6,    /* workspace too small */
+    HVLM_ERR_UNSUPPORTED = -7
+} hvlm_status;
+
+typedef enum { HVLM_F32 = 0, HVLM_BF16 = 1, HVLM_F16 = 2 } hvlm_dtype;
+
+/* video_arch / video_compress_mode  (lita/model/lita_arch.py:41-75, hoi_forecast/model/visual_to_tokens.py:230-272) */
+typedef enum {
+    HVLM_POOL_TEMPORAL_SPATIAL_POOL = 0, /* [t fast means] ++ [4 frames x 8x8 2x2-avg]  -> t+256 tokens */
+    HVLM_POOL_SPATIAL_POOL = 1,          /* slow tokens only                             -> 256 tokens   */
+    HVLM_POOL_TEMPORAL = 2,              /* mean over the 256 tokens of each frame       -> t tokens     */
+    HVLM_POOL_SPATIAL = 3,               /* mean over frames                             -> 256 tokens   */
+    HVLM_POOL_TEMPORAL_SPATIAL = 4       /* temporal ++ spatial                          -> t+256 tokens */
+} hvlm_pool_mode;
+
+/* which prepare_inputs_labels_for_multimodal is being replaced */
+typedef enum {
+    HVLM_SPLICE_LLAVA = 0,      /* llava/model/llava_arch.py:110-234  (mask NOT position-spliced)          */
+    HVLM_SPLICE_HANDSONVLM = 1  /* handsonvlm/model/language_model/handsonvlm.py:212-451 (mask spliced,    */
+                                /* hand positional embeddings added at <hand_traj> rows of the tail)       */
+} hvlm_splice_variant;
+
+/* GEMM epilogues (C = A * B^T, A [M,K] bf16 row-major, B [N,K] bf16 row-major) */
+typedef enum {
+    HVLM_EPI_BIAS = 0,          /* out = acc + bias[n]                                   */
+    HVLM_EPI_BIAS_QUICKGELU = 1,/* out = g(acc + bias[n]), g(x) = x * sigmoid(1.702 x)   */
+    HVLM_EPI_BIAS_RESIDUAL = 2  /* out = resid[m,n] + acc + bias[n]  (out may alias resid) */
+} hvlm_epilogue;
+
+HVLM_API const char* hvlm_strerror(int status);
+HVLM_API int hvlm_abi_version(void);
+/* 0 if `device` is an sm_100 GPU this library can run on, else HVLM_ERR_CUDA. */
+HVLM_API int hvlm_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM  -- replaces every nn.Linear on the path:
+ *   mm_projector                           llava/model/llava_arch.py:33,92 ; visual_to_tokens.py:279
+ *   CLIP q/k/v/out_proj, fc1, fc2          transformers CLIPEncoderLayer (clip_encoder.py:48)
+ *   projector wgrad (dW = dY^T X)          autograd of the above (training-shaped variant)
+ * bias may be NULL (treated as 0).  N % 128 == 0, K % 8 == 0 (K tail < 64 is zero-filled by TMA).
+ * out_dtype: HVLM_BF16 or HVLM_F32.  resid (fp32 [M,N]) only for HVLM_EPI_BIAS_RESIDUAL.
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API int hvlm_gemm_bf16(const void* A, const void* B, const float* bias, const float* resid, void* out, int M, int N,
+                   int K, int epilogue, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIP ViT-L/14 tower -- replaces CLIPVisionTower.forward
+ *   llava/model/multimodal_encoder/clip_encoder.py:39-51 (+ feature_select :29-37)
+ * Fixed architecture: hidden 1024, 16 heads x 64, MLP 4096, 224x224 / patch 14 -> 257 tokens,
+ * quick-GELU, LayerNorm eps 1e-5.  bf16 GEMM regime with an fp32 residual stream, fp32 LayerNorm
+ * statistics and fp32 softmax.
+ *
+ * Weights live in ONE device blob whose layout is defined here (hvlm_vit_layout); the host side fills
+ * it once from the HF-named state dict (q_proj weight/bias pre-scaled by 64^-1/2, exact in bf16).
+ * ---------------------------------------------------------------------------------------------- */
+#define HVLM_VIT_HIDDEN 1024
+#define HVLM_VIT_HEADS 16
+#define HVLM_VIT_HEAD_DIM 64
+#define HVLM_VIT_MLP 4096
+#define HVLM_VIT_PATCH 14
+#define HVLM_VIT_IMAGE 224
+#define HVLM_VIT_TOKENS 257      /* CLS + 256 patches */
+#define HVLM_VIT_PATCHES 256
+#define HVLM_VIT_PATCH_K 588     /* 3*14*14 */
+#define HVLM_VIT_PATCH_KPAD 640  /* padded to a multiple of 64 with zeros */
+#define HVLM_VIT_MAX_LAYERS 24
+
+typedef struct {
+    /* byte offsets into the blob */
+    uint64_t patch_w;   /* bf16 [1024, 640]   conv weight reshaped [E, c*196+i*14+j], zero padded */
+    uint64_t cls;       /* f32  [1024]        class_embedding                                   */
+    uint64_t pos;       /* f32  [257, 1024]   position_embedding.weight                          */
+    uint64_t pre_ln_g;  /* f32  [1024]        pre_layrnorm.weight   (sic, HF spelling)           */
+    uint64_t pre_ln_b;  /* f32  [1024] */
+    struct {
+        uint64_t ln1_g, ln1_b; /* f32 [1024]                                                      */
+        uint64_t w_qkv;        /* bf16 [3072,1024] rows: q (pre-scaled 1/8) | k | v                */
+        uint64_t b_qkv;        /* f32 [3072]                                                      */
+        uint64_t w_o, b_o;     /* bf16 [1024,1024], f32 [1024]                                    */
+        uint64_t ln2_g, ln2_b; /* f32 [1024]                                                      */
+        uint64_t w_fc1, b_fc1; /* bf16 [4096,1024], f32 [4096]                                    */
+        uint64_t w_fc2, b_fc2; /* bf16 [1024,4096], f32 [1024]                                    */
+    } layer[HVLM_VIT_MAX_LAYERS];
+    uint64_t total_bytes;
+    int32_t n_layers;
+    int32_t _pad;
+} hvlm_vit_layout;
+
+HVLM_API int hvlm_vit_l14_layout(int n_layers, hvlm_vit_layout* out_host);
+/* workspace needed for `n_frames` frames (bytes). */
+HVLM_API size_t hvlm_vit_l14_workspace_bytes(int n_frames);
+/*
+ * pixels  [n_frames,3,224,224] NCHW, pix_dtype f32|bf16|f16
+ * hidden  f32 [n_frames,257,1024]: residual stream after `n_layers_run` encoder layers == HF
+ *         hidden_states[n_layers_run]; select_layer=-2 of the 24-layer tower => n_layers_run = 23
+ *         (layer 24 and post_layernorm are never computed).  feature_select 'patch' = rows 1..256.
+ */
+HVLM_API int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype, int n_frames,
+                     float* hidden, void* workspace, size_t workspace_bytes, void* stream);
+/* hidden f32 [n,257,1024] -> feats [n,256,1024] (drop CLS) cast to out_dtype (clip_encoder.py:31-32,49). */
+HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls, void* stream);
+
+/* building blocks of the tower, exported for per-stage parity tests */
+HVLM_API int hvlm_layernorm_1024(const float* x, const float* gamma, const float* beta, void* out, int rows, int out_dtype,
+                        float eps, void* stream);
+/* A [M=n_frames*257,1024] bf16 -> q,k [n_frames,16,257,64] bf16 ; vt [n_frames,16,64,272] bf16 (keys padded) */
+HVLM_API int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* b_qkv, void* q, void* k, void* vt,
+                      int n_frames, void* stream);
+/* softmax(q k^T) v per (frame, head); q already carries the 64^-1/2 scale. out bf16 [n_frames*257, 1024] */
+HVLM_API int hvlm_vit_attention(const void* q, const void* k, const void* vt, void* out, int n_frames, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LITA slow-fast token pooling -- replaces
+ *   LitaMetaForCausalLM.videos_to_tokens pooling branch     lita/model/lita_arch.py:41-73
+ *   VisualToTokenHelper.compress_tokens                     hoi_forecast/model/visual_to_tokens.py:230-272
+ * tok  [B, t, *, C]: element (b,f,s,c) at ((b*t+f)*frame_stride + s)*C + c  (frame_stride >= 256 lets the
+ *      kernel read rows 1..256 of the tower's [*,257,1024] hidden state in place: pass hidden + 1024).
+ * out  [B, n_out, C], n_out per hvlm_pool_mode.  Each input element is read exactly once.
+ * fp32 accumulation; in/out dtype f32 or bf16.  C % 8 == 0.  t >= 1.
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API int hvlm_pool_out_tokens(int t, int mode);
+HVLM_API int hvlm_pool_slowfast_fwd(const void* tok, int in_dtype, int64_t frame_stride, void* out, int out_dtype, int B,
+                           int t, int C, int mode, void* stream);
+/* d_tok [B,t,256,C] (dense) = autograd of the above wrt tok; dout [B,n_out,C]. */
+HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok, int dtok_dtype, int B, int t, int C,
+                           int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Token splice -- replaces prepare_inputs_labels_for_multimodal
+ *   llava/model/llava_arch.py:110-234            (HVLM_SPLICE_LLAVA)
+ *   handsonvlm/.../handsonvlm.py:212-451         (HVLM_SPLICE_HANDSONVLM)
+ * Step 1  hvlm_splice_count : per-sample number of IMAGE_TOKEN_INDEX (-200) tokens (device int32 [B]).
+ * Step 2  hvlm_splice_plan  : index plan.  src_index [B,L] int32: >=0 text position p (row = ids[b,p]);
+ *                             -(1+g) visual row g of visual[n_img*Nv, D]; INT32_MIN = padding.
+ *                             hand_code [B,L] int8: -1 or k = which hand positional embedding is added.
+ *                             lens [B] int32 = spliced length of each sample.  status: device int32, error bits
+ *                             OR-ed in (HVLM_PLAN_*).  Image-slot bookkeeping follows cur_image_idx
+ *                             (a sample without image token still consumes a slot).
+ * Step 3  hvlm_splice_fwd   : index-driven row gather into embeds [B,L,D] (+ labels [B,L] i64, mask [B,L] u8),
+ *                             fusing the embedding lookup (embed_tokens) and the sinusoidal hand embedding
+ *                             (process_traj_positional_embedding, handsonvlm.py:310-338).
+ * L is chosen by the caller: T-1+Nv when every sample has exactly one image token (the collator's
+ * contract, hybrid_dataset.py:155-158), else max(lens) after reading `lens` back.
+ * ---------------------------------------------------------------------------------------------- */
+#define HVLM_IGNORE_INDEX (-100)
+#define HVLM_IMAGE_TOKEN_INDEX (-200)
+#define HVLM_HAND_TRAJ_TOKEN_ID 32100
+
+#define HVLM_PLAN_ERR_LEN_OVERFLOW 1    /* a spliced sample is longer than L                      */
+#define HVLM_PLAN_ERR_IMG_OVERFLOW 2    /* more image slots consumed than n_img                   */
+#define HVLM_PLAN_ERR_HAND_COUNT 4      /* training: >4 hand tokens; eval: count != n_hand points */
+#define HVLM_PLAN_ERR_BAD_ID 8          /* token id outside [0,vocab) (and not -200)              */
+#define HVLM_PLAN_NOT_UNIFORM 16        /* lens differ between samples (ragged output)            */
+
+HVLM_API int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* counts, void* stream);
+HVLM_API int hvlm_splice_plan(const int64_t* ids, const int32_t* counts /*from hvlm_splice_count*/, int B, int T, int Nv,
+                     int n_img, int L, int vocab, int variant,
+                     int hand_mode /*0 none, 1 training (4 points, cnt/4 scaling), 2 eval (n points)*/,
+                     int n_hand_points, int32_t* src_index, int8_t* hand_code, int32_t* lens,
+                     float* hand_scale /*[B]*/, int32_t* status, void* stream);
+HVLM_API int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens, const float* hand_scale,
+                    const int64_t* ids, const int64_t* labels /*NULL ok*/, const uint8_t* mask /*NULL ok*/,
+                    const void* embed_table, const void* visual, const uint8_t* visual_mask /*NULL = all true*/,
+                    const float* future_hands /*[B,2,n,2] f32 or NULL*/, int n_hand_points, int B, int T, int L,
+                    int Nv, int D, int dtype, int variant, void* out_embeds, int64_t* out_labels,
+                    uint8_t* out_mask, void* stream);
+/* backward of the copy: d_visual [n_img*Nv, D] f32 (written, each row at most once) and scatter-ADD of the text
+ * rows into d_embed_table [vocab, D] f32 (atomics; caller zero-initialises).  Either output may be NULL. */
+HVLM_API int hvlm_splice_bwd(const void* d_embeds, int dtype, const int32_t* src_index, const int64_t* ids, int B, int T,
+                    int L, int n_visual_rows, int D, float* d_visual, float* d_embed_table, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * <hand_traj> hidden-state gather -- replaces the inline loop of HandsOnVLMForCausalLM.forward
+ *   handsonvlm/.../handsonvlm.py:146-187  and the generation-time gather :609-622
+ * rows[b,k] = k-th position i with labels[b,i+1] == hand_id (i.e. the state that predicts the token);
+ * out[b,h,k,j] = hidden[b, rows[b,k], 2j+h]; samples without hand tokens give zeros and valid[b]=0.
+ * counts[b] = number of such positions (must be 0 or 4 in the reference; the caller decides how to react).
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API int hvlm_hand_gather_fwd(const void* hidden, int dtype, const int64_t* labels, int64_t hand_id, int B, int L, int D,
+                         void* out, uint8_t* valid, int32_t* rows /*[B,4]*/, int32_t* counts /*[B]*/, void* stream);
+/* d_hidden [B,L,D] f32 += scatter of dout [B,2,4,D/2]; caller zero-initialises d_hidden. */
+HVLM_API int hvlm_hand_gather_bwd(const void* dout, int dtype, const int32_t* rows, int B, int L, int D, float* d_hidden,
+                         void* stream);
+/* generation step: hidden_last [B,D] -> out [B,2,1,D/2] (even/odd de-interleave). */
+HVLM_API int hvlm_hand_gather_step(const void* hidden_last, int dtype, int B, int D, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * helpers for the training-shaped variant
+ * ---------------------------------------------------------------------------------------------- */
+/* out bf16 [C, R_pad] = in[R, C]^T (zero padded to R_pad, a multiple of 8): makes dY / X K-major for wgrad. */
+HVLM_API int hvlm_transpose_to_bf16(const void* in, int in_dtype, void* out, int R, int C, int R_pad, void* stream);
+/* db[n] = sum_m dY[m,n]  (fp32) */
+HVLM_API int hvlm_colsum(const void* dy, int dtype, float* db, int M, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVLM_B200_H */

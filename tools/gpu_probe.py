@@ -1,0 +1,232 @@
+"""GPU bring-up probe: runs one stage of the CUDA path against the oracle and prints error statistics.
+Usage (on the GPU box):  timeout 300 python tools/gpu_probe.py <stage> ;  stages: simple gemm attn vit bench
+Each stage is a separate process so that a hang in one kernel cannot take the others down."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import hvlm_b200  # noqa: E402
+from hvlm_b200 import ops  # noqa: E402
+from oracle import restate, synth  # noqa: E402
+
+dev = torch.device("cuda:0")
+RES = {}
+
+
+def stats(name, a, b):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    d = (a - b).abs()
+    r = dict(max_abs=float(d.max()), ref_max=float(b.abs().max()), rel=float(d.max() / b.abs().max().clamp_min(1e-30)),
+             mean_rel=float(d.mean() / b.abs().mean().clamp_min(1e-30)), nan=int(torch.isnan(a).sum()))
+    RES[name] = r
+    print(f"{name:40s} rel={r['rel']:.3e} mean_rel={r['mean_rel']:.3e} max_abs={r['max_abs']:.3e} nan={r['nan']}", flush=True)
+    return r
+
+
+def stage_simple():
+    # layernorm
+    x = synth.gen("ln.x", (777, 1024), 2.0, 1, 0.3)
+    g = synth.gen("ln.g", (1024,), 0.2, 1, 1.0)
+    b = synth.gen("ln.b", (1024,), 0.1, 1)
+    ref = torch.nn.functional.layer_norm(x, (1024,), g, b, 1e-5)
+    stats("layernorm_f32", ops.layernorm_1024(x.to(dev), g.to(dev), b.to(dev), torch.float32), ref)
+    stats("layernorm_bf16", ops.layernorm_1024(x.to(dev), g.to(dev), b.to(dev), torch.bfloat16), ref)
+    # pooling
+    for t, C, dt in ((100, 1024, torch.float32), (10, 4096, torch.float32), (2, 64, torch.float32), (100, 1024, torch.bfloat16)):
+        tok = synth.gen(f"pool{t}", (2, t, 256, C), 1.0, 2)
+        for mode in ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temporal_spatial"):
+            ref = restate.pool_tokens(tok.to(dt).float(), mode)
+            out = ops.pool_tokens(tok.to(dev).to(dt), mode, torch.float32)
+            stats(f"pool_{mode}_t{t}_C{C}_{str(dt)[6:]}", out, ref)
+    dout = synth.gen("pooldout", (2, 266, 512), 1.0, 3)
+    ref = restate.pool_tokens_backward(dout, 10)
+    stats("pool_bwd", ops.pool_slowfast_bwd(dout.to(dev), 10, 0, False), ref)
+    # in-place read of the tower layout: frame_stride 257, row offset 1
+    hid = synth.gen("hid", (6, 257, 1024), 1.0, 4)
+    ref = restate.pool_tokens(hid[:, 1:].reshape(2, 3, 256, 1024), "temporal_spatial_pool")
+    stats("pool_strided", ops.pool_slowfast(hid.to(dev), 2, 3, 257, 1, 0, False), ref)
+    # gather
+    hidden = synth.gen("gh", (4, 40, 64), 1.0, 41)
+    labels = torch.full((4, 40), -100, dtype=torch.int64)
+    labels[0, 30:34] = 32100
+    labels[1, [3, 9, 17, 39]] = 32100
+    labels[3, 1:5] = 32100
+    ro, rv, rr = restate.gather_hand_traj(hidden, labels)
+    o, v, r, c = ops.hand_gather(hidden.to(dev), labels.to(dev), 32100)
+    stats("gather", o, ro)
+    print("gather valid/rows/counts eq:", torch.equal(v.cpu(), rv), torch.equal(r.cpu(), rr), c.tolist())
+    RES["gather_exact"] = bool(torch.equal(o.cpu(), ro) and torch.equal(v.cpu(), rv) and torch.equal(r.cpu(), rr))
+    # splice
+    from hvlm_b200 import _lib as L
+    D = 256
+    table = synth.embed_table(D)
+    vis = synth.gen("vis", (3, 356, D), 1.0, 5)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=3, seed=22, ragged=True)
+    rm, re_, rl = restate.splice(ids, mask, labels, vis, table, "handsonvlm", future_hands=fh)
+    idsd = ids.to(dev)
+    counts = ops.splice_count(idsd)
+    Lout = ids.shape[1] - 1 + 356
+    plan = ops.splice_plan(idsd, counts, 356, 3, Lout, table.shape[0], L.SPLICE_HANDSONVLM, 1, 4)
+    e, l2, m2 = ops.splice_gather(plan[0], plan[1], plan[2], plan[3], idsd, labels.to(dev), mask.to(dev), table.to(dev),
+                                  vis.to(dev), None, fh.to(dev), L.SPLICE_HANDSONVLM)
+    stats("splice_embeds", e, re_)
+    RES["splice_exact"] = bool(torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm))
+    print("splice labels/mask eq:", torch.equal(l2.cpu(), rl), torch.equal(m2.cpu(), rm), "status", int(plan[4].item()),
+          "counts", counts.tolist())
+
+
+def stage_gemm():
+    torch.manual_seed(0)
+    cases = [(128, 256, 64), (128, 256, 1024), (256, 512, 128), (300, 1024, 1024), (25700, 3072, 1024),
+             (1000, 4096, 1024), (1000, 1024, 4096), (356, 4096, 1024), (356, 5120, 1024), (200, 128, 64),
+             (4096, 1024, 1424)]
+    for (M, N, K) in cases:
+        a = synth.gen(f"A{M}", (M, K), 1.0, 1).to(torch.bfloat16)
+        w = synth.gen(f"W{N}", (N, K), K ** -0.5, 1).to(torch.bfloat16)
+        bias = synth.gen(f"b{N}", (N,), 0.5, 1)
+        ad, wd, bd = a.to(dev), w.to(dev), bias.to(dev)
+        ref = (ad.float() @ wd.float().t() + bd).cpu()
+        stats(f"gemm_f32_{M}x{N}x{K}", ops.gemm(ad, wd, bd, out_dtype=torch.float32), ref)
+        if M <= 1000:
+            stats(f"gemm_bf16_{M}x{N}x{K}", ops.gemm(ad, wd, bd, out_dtype=torch.bfloat16), ref)
+            stats(f"gemm_gelu_{M}x{N}x{K}", ops.gemm(ad, wd, bd, epilogue="quick_gelu", out_dtype=torch.float32),
+                  restate.quick_gelu(ref))
+            res = synth.gen(f"r{M}", (M, N), 1.0, 2).to(dev)
+            stats(f"gemm_resid_{M}x{N}x{K}", ops.gemm(ad, wd, bd, epilogue="residual", resid=res, out_dtype=torch.float32),
+                  ref + res.cpu())
+    # timing of the big ones
+    for (M, N, K) in ((25700, 3072, 1024), (25700, 4096, 1024), (25700, 1024, 4096), (25700, 1024, 1024)):
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        for _ in range(3):
+            ops.gemm(a, w, bias, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.gemm(a, w, bias, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tf = 2 * M * N * K / ms / 1e9
+        e0.record()
+        for _ in range(10):
+            torch.nn.functional.linear(a, w)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 10
+        RES[f"time_gemm_{M}x{N}x{K}"] = dict(ms=ms, tflops=tf, cublas_ms=ms2, cublas_tflops=2 * M * N * K / ms2 / 1e9)
+        print(f"gemm {M}x{N}x{K}: {ms:.3f} ms {tf:.0f} TF/s | cublas {ms2:.3f} ms {2*M*N*K/ms2/1e9:.0f} TF/s", flush=True)
+
+
+def _attn_ref(q, k, v):
+    # q,k,v [F,16,257,64] fp32 (q pre-scaled)
+    s = q @ k.transpose(-1, -2)
+    return torch.softmax(s, -1) @ v
+
+
+def stage_attn():
+    F = 3
+    y = synth.gen("attn.y", (F * 257, 1024), 1.0, 1).to(torch.bfloat16)
+    w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
+    w[:1024] *= 0.125
+    b = synth.gen("attn.b", (3072,), 0.1, 1)
+    q, k, vt = ops.vit_qkv(y.to(dev), w.to(dev), b.to(dev), F)
+    ref = (y.float() @ w.float().t() + b).reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)   # [3,F,16,257,64]
+    stats("qkv_q", q, ref[0])
+    stats("qkv_k", k, ref[1])
+    stats("qkv_vt", vt[..., :257], ref[2].transpose(-1, -2))
+    print("vt pad zero:", float(vt[..., 257:].abs().max()))
+    qf, kf, vf = q.float().cpu(), k.float().cpu(), vt[..., :257].float().cpu().transpose(-1, -2)
+    o = ops.vit_attention(q, k, vt)
+    oref = _attn_ref(qf, kf, vf).permute(0, 2, 1, 3).reshape(F * 257, 1024)
+    stats("attention", o, oref)
+    # sharper distribution
+    q2 = (q.float() * 6).to(torch.bfloat16)
+    o2 = ops.vit_attention(q2, k, vt)
+    stats("attention_sharp", o2, _attn_ref(q2.float().cpu(), kf, vf).permute(0, 2, 1, 3).reshape(F * 257, 1024))
+    Fb = 100
+    qb = torch.randn(Fb, 16, 257, 64, device=dev).to(torch.bfloat16) * 0.3
+    kb = torch.randn(Fb, 16, 257, 64, device=dev).to(torch.bfloat16)
+    vb = torch.zeros(Fb, 16, 64, 272, device=dev, dtype=torch.bfloat16)
+    vb[..., :257] = torch.randn(Fb, 16, 64, 257, device=dev).to(torch.bfloat16)
+    for _ in range(3):
+        ob = ops.vit_attention(qb, kb, vb)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.vit_attention(qb, kb, vb)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    RES["time_attn_100f"] = dict(ms=ms, tflops=Fb * 16 * 4 * 257 * 257 * 64 / ms / 1e9)
+    print(f"attention 100 frames: {ms:.3f} ms", flush=True)
+    stats("attention_big_vs_sdpa", ob.reshape(Fb, 257, 16, 64).permute(0, 2, 1, 3),
+          torch.nn.functional.scaled_dot_product_attention(qb.float(), kb.float(), vb[..., :257].float().transpose(-1, -2), scale=1.0))
+
+
+def stage_vit():
+    from hvlm_b200.tower import CLIPVisionTower
+    for profile, nl, nf in (("strong", 2, 2), ("strong", 23, 2), ("hf", 23, 3)):
+        sd = synth.clip_state_dict(synth.VIT_L14, 0, profile, n_layers=nl)
+        px = synth.pixels((nf, 3, 224, 224), seed=3)
+        tower = CLIPVisionTower("synthetic", None, delay_load=True)
+        tower.select_layer = nl
+        tower.load_model(sd)
+        tower = tower.to(dev)
+        t0 = time.time()
+        hid = tower.forward_hidden(px.to(dev))
+        torch.cuda.synchronize()
+        ref = restate.vit_hidden(px, sd, nl)
+        stats(f"vit_{profile}_{nl}L_hidden", hid, ref)
+        emu = restate.vit_hidden(px, sd, nl, emulate="bf16")
+        stats(f"vit_{profile}_{nl}L_vs_bf16emu", hid, emu)
+        stats(f"vit_{profile}_{nl}L_emu_vs_fp32", emu, ref)
+        feats = tower(px.to(dev))
+        stats(f"vit_{profile}_{nl}L_feats", feats, ref[:, 1:])
+
+
+def stage_bench():
+    from hvlm_b200.tower import CLIPVisionTower
+    sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=23)
+    tower = CLIPVisionTower("synthetic", None, delay_load=True)
+    tower.load_model(sd)
+    tower = tower.to(dev)
+    px = torch.randn(100, 3, 224, 224, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        tower.forward_hidden(px)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        tower.forward_hidden(px)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    RES["time_vit_100f"] = dict(ms=ms, frames_per_s=100 / ms * 1e3, tflops=100 * 155.29 / ms)
+    print(f"ViT 100 frames: {ms:.2f} ms  {100/ms*1e3:.0f} frames/s  {100*155.29/ms:.0f} TF/s", flush=True)
+
+
+if __name__ == "__main__":
+    stage = sys.argv[1]
+    t0 = time.time()
+    try:
+        {"simple": stage_simple, "gemm": stage_gemm, "attn": stage_attn, "vit": stage_vit, "bench": stage_bench}[stage]()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa
+        import traceback
+        traceback.print_exc()
+        RES["exception"] = repr(e)
+    RES["seconds"] = time.time() - t0
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"probe_{stage}.json"), "w") as f:
+        json.dump(RES, f, indent=1)
