@@ -1,7 +1,7 @@
 """ctypes binding of libhvlm_b200.so -- the C ABI declared in include/hvlm_b200.h.
 
 The product path has NO fallback: if the shared library is missing or the device is not an sm_100 GPU the
-import of the compute ops fails loudly (RuntimeError), it never routes to torch eager or to oracle/.
+import of the compute ops fails loudly (RuntimeError), it never routes to torch eager or to any CPU restatement.
 """
 from __future__ import annotations
 

@@ -1,0 +1,95 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/hvlm_b200.h declares;
+argument validation works without a GPU; the product path refuses to run without CUDA (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import hvlm_b200
+from hvlm_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(L.LIB_PATH):
+        hvlm_b200.build()
+    return L.lib()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "hvlm_b200.h")).read()
+    return sorted(set(re.findall(r"HVLM_API\s+[\w\s\*]+?\b(hvlm_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in hvlm_b200.h but not exported"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature"
+    assert sorted(L.SIGNATURES) == syms
+
+
+def test_version_and_strerror(lib):
+    assert lib.hvlm_abi_version() == 1
+    assert L.strerror(0) == "ok"
+    assert "aligned" in L.strerror(-4)
+    assert "unknown" in L.strerror(-99)
+
+
+def test_pool_out_tokens(lib):
+    assert lib.hvlm_pool_out_tokens(100, 0) == 356
+    assert lib.hvlm_pool_out_tokens(100, 1) == 256
+    assert lib.hvlm_pool_out_tokens(10, 2) == 10
+    assert lib.hvlm_pool_out_tokens(10, 9) < 0
+
+
+def test_vit_layout_is_consistent(lib):
+    lay = L.VitLayout()
+    assert lib.hvlm_vit_l14_layout(23, C.byref(lay)) == 0
+    assert lay.n_layers == 23
+    # 23 layers x 12.6 M params (bf16) + embeddings; offsets strictly increasing and 256-byte aligned
+    offs = [lay.patch_w, lay.cls, lay.pos, lay.pre_ln_g, lay.pre_ln_b]
+    for l in range(23):
+        y = lay.layer[l]
+        offs += [y.ln1_g, y.ln1_b, y.w_qkv, y.b_qkv, y.w_o, y.b_o, y.ln2_g, y.ln2_b, y.w_fc1, y.b_fc1, y.w_fc2, y.b_fc2]
+    assert all(b > a for a, b in zip(offs, offs[1:])) and all(o % 256 == 0 for o in offs)
+    assert 570e6 < lay.total_bytes < 600e6
+    lay24 = L.VitLayout()
+    assert lib.hvlm_vit_l14_layout(24, C.byref(lay24)) == 0
+    assert lay24.layer[5].w_fc1 == lay.layer[5].w_fc1          # prefix property: fewer layers can run from one blob
+    assert lib.hvlm_vit_l14_layout(25, C.byref(lay)) == L.lib().hvlm_vit_l14_layout(-1, C.byref(lay)) < 0
+    assert lib.hvlm_vit_l14_workspace_bytes(100) > 400e6
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    null = C.c_void_p(0)
+    assert lib.hvlm_gemm_bf16(null, null, null, null, null, 1, 1, 1, 0, 1, null) == -1
+    assert lib.hvlm_pool_slowfast_fwd(null, 0, 256, null, 0, 1, 1, 8, 0, null) == -1
+    assert lib.hvlm_hand_gather_fwd(null, 0, null, 32100, 1, 1, 2, null, null, null, null, null) == -1
+    assert lib.hvlm_splice_count(null, 1, 1, null, null) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+    from hvlm_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.pool_tokens(torch.zeros(1, 2, 256, 8), "temporal_spatial_pool")
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(128, 8, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        ops.ensure_device()
+    assert L.lib().hvlm_device_check(0) == -5
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "handsonvlm-release_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./]", txt, re.M), f"{f} references oracle/"

@@ -1,0 +1,489 @@
+"""GPU parity tests: every CUDA stage against the CPU oracle (oracle/restate.py, pinned to the real reference by
+tests/golden) and directly against the golden fixtures.  All calls go through the C ABI (ctypes -> libhvlm_b200.so).
+
+Tolerances (BASELINE.json north_star):
+  * ints / bools / copied rows : bit-exact (torch.equal)
+  * fp32 pooling               : max|a-b| / max|b| <= 1e-5
+  * bf16-GEMM-backed outputs   : max|a-b| / max|b_fp32| <= 1e-2 against the fp32 oracle
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import hvlm_b200
+from hvlm_b200 import _lib as L
+from hvlm_b200 import arch, ops
+from hvlm_b200.tower import CLIPVisionTower
+from oracle import restate, synth
+from oracle.make_golden import SMALL, SMALL_D, small_parts
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_POOL = 1e-5
+TOL_BF16 = 1e-2
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def relmax(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ GEMM (tcgen05)
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 1024, 1024), (356, 4096, 1024), (356, 5120, 1024),
+                                   (1000, 1024, 4096), (200, 128, 64), (2571, 3072, 1024), (1024, 1024, 1424)])
+def test_gemm_epilogues(M, N, K):
+    a = synth.gen(f"A{M}", (M, K), 1.0, 1).to(torch.bfloat16).to(DEV)
+    w = synth.gen(f"W{N}", (N, K), K ** -0.5, 1).to(torch.bfloat16).to(DEV)
+    bias = synth.gen(f"b{N}", (N,), 0.5, 1).to(DEV)
+    res = synth.gen(f"r{M}", (M, N), 1.0, 2).to(DEV)
+    ref = a.float() @ w.float().t() + bias                     # same bf16 operands, fp32 math
+    assert relmax(ops.gemm(a, w, bias, out_dtype=torch.float32), ref) <= 2e-5
+    assert relmax(ops.gemm(a, w, None, out_dtype=torch.float32), ref - bias) <= 2e-5
+    assert relmax(ops.gemm(a, w, bias, out_dtype=torch.bfloat16), ref) <= 5e-3
+    assert relmax(ops.gemm(a, w, bias, epilogue="quick_gelu", out_dtype=torch.float32), restate.quick_gelu(ref)) <= 2e-5
+    assert relmax(ops.gemm(a, w, bias, epilogue="residual", resid=res, out_dtype=torch.float32), ref + res) <= 2e-5
+    # in-place residual (how the tower uses it)
+    r2 = res.clone()
+    ops.gemm(a, w, bias, epilogue="residual", resid=r2, out=r2)
+    assert relmax(r2, ref + res) <= 2e-5
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(L.HvlmError):
+        ops.gemm(a, torch.zeros(100, 64, dtype=torch.bfloat16, device=DEV))      # N % 128 != 0
+    with pytest.raises(AssertionError):
+        ops.gemm(a.float(), a.float())
+
+
+def test_projector_autograd_matches_torch():
+    M, D = 712, 4096
+    x = synth.gen("proj.x", (M, 1024), 1.0, 3).to(DEV)
+    ps = synth.projector_state(D)
+    w = ps["mm_projector.weight"].to(DEV).requires_grad_(True)
+    b = ps["mm_projector.bias"].to(DEV).requires_grad_(True)
+    dy = synth.gen("proj.dy", (M, D), 1.0, 3).to(DEV)
+    y = ops.linear(x, w.to(torch.bfloat16), b, True)
+    y.backward(dy)
+    xr = x.to(torch.bfloat16).float()
+    wr = w.detach().to(torch.bfloat16).float()
+    assert relmax(y, xr @ wr.t() + b.detach()) <= 2e-5
+    assert relmax(w.grad, dy.t() @ x) <= TOL_BF16              # fp32 oracle
+    assert relmax(b.grad, dy.sum(0)) <= 1e-5
+
+
+# ------------------------------------------------------------------ LayerNorm
+def test_layernorm():
+    x = synth.gen("ln.x", (1030, 1024), 2.0, 1, 0.3)
+    g = synth.gen("ln.g", (1024,), 0.2, 1, 1.0)
+    b = synth.gen("ln.b", (1024,), 0.1, 1)
+    ref = torch.nn.functional.layer_norm(x, (1024,), g, b, 1e-5)
+    assert relmax(ops.layernorm_1024(x.to(DEV), g.to(DEV), b.to(DEV), torch.float32), ref) <= 1e-5
+    assert relmax(ops.layernorm_1024(x.to(DEV), g.to(DEV), b.to(DEV), torch.bfloat16), ref) <= 5e-3
+
+
+# ------------------------------------------------------------------ pooling
+@pytest.mark.parametrize("t,d", [(100, 32), (10, 16), (2, 8), (5, 8)])
+@pytest.mark.parametrize("mode", ["temporal_spatial_pool", "spatial_pool"])
+def test_pool_matches_reference_fixture(golden, t, d, mode):
+    g = golden(f"pool_{mode}_t{t}")
+    tok = synth.gen(f"pooltok{t}", (2, t, 256, d), 1.0, seed=5)
+    out = ops.pool_tokens(tok.to(DEV), mode)
+    assert relmax(out, T(g["out"])) <= TOL_POOL
+
+
+@pytest.mark.parametrize("mode", ["temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temporal_spatial"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool_modes_vs_oracle(mode, dtype):
+    tok = synth.gen("pool.modes", (2, 7, 256, 1024), 1.0, 2).to(dtype)
+    ref = restate.pool_tokens(tok.float(), mode)
+    assert relmax(ops.pool_tokens(tok.to(DEV), mode, torch.float32), ref) <= TOL_POOL
+
+
+def test_pool_reads_tower_layout_in_place():
+    hid = synth.gen("hid", (6, 257, 1024), 1.0, 4)
+    ref = restate.pool_tokens(hid[:, 1:].reshape(2, 3, 256, 1024), "temporal_spatial_pool")
+    assert relmax(ops.pool_slowfast(hid.to(DEV), 2, 3, 257, 1, 0, False), ref) <= TOL_POOL
+
+
+def test_pool_backward_fixture_and_autograd(golden):
+    g = golden("pool_bwd_t10")
+    dout = synth.gen("pooldout_bwd", (1, 266, 8), 1.0, seed=6)
+    assert relmax(ops.pool_slowfast_bwd(dout.to(DEV), 10, 0, False), T(g["dtok"])) <= TOL_POOL
+    tok = synth.gen("pooltok_bwd", (1, 10, 256, 8), 1.0, seed=6).to(DEV).requires_grad_(True)
+    out = ops.pool_tokens(tok, "temporal_spatial_pool")
+    (out * dout.to(DEV)).sum().backward()
+    assert relmax(tok.grad, T(g["dtok"])) <= TOL_POOL
+
+
+def test_pool_full_size_properties():
+    """BASELINE size (fp32, 100 frames, C=4096): linearity and mean-of-means, size-independent checks."""
+    a = torch.randn(1, 100, 256, 4096, device=DEV)
+    b = torch.randn(1, 100, 256, 4096, device=DEV)
+    pa, pb = ops.pool_tokens(a, "temporal_spatial_pool"), ops.pool_tokens(b, "temporal_spatial_pool")
+    pab = ops.pool_tokens(a + 2 * b, "temporal_spatial_pool")
+    assert pa.shape == (1, 356, 4096)
+    assert relmax(pab, pa + 2 * pb) <= 1e-5
+    # each selected frame's 64 slow tokens average to that frame's fast token
+    for k, f in enumerate([0, 33, 66, 99]):
+        assert relmax(pa[0, 100 + 64 * k: 100 + 64 * (k + 1)].mean(0), pa[0, f]) <= 1e-5
+    assert relmax(pa[0, :100], a[0].mean(1)) <= 1e-5
+
+
+# ------------------------------------------------------------------ gather
+@pytest.mark.parametrize("name,shape,seedname,seed", [("gather_toy", None, None, None),
+                                                      ("gather_rand", (4, 40, 64), "gather_hidden", 41),
+                                                      ("gather_pos0", (1, 12, 16), "gather_hidden0", 42)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gather_matches_reference_fixture(golden, name, shape, seedname, seed, dtype):
+    g = golden(name)
+    labels = T(g["labels"])
+    hidden = (torch.arange(2 * 10 * 8, dtype=torch.float32).reshape(2, 10, 8) if shape is None
+              else synth.gen(seedname, shape, 1.0, seed=seed)).to(dtype)
+    fv = torch.ones(labels.shape[0], 2, dtype=torch.bool, device=DEV)
+    out, valid = arch.gather_hand_traj_states(hidden.to(DEV), labels.to(DEV), future_valid=fv)
+    assert torch.equal(out.cpu().float(), T(g["out"]).to(dtype).float())
+    assert torch.equal(fv.cpu(), T(g["future_valid"]))
+
+
+def test_gather_wrong_count_raises_like_reference():
+    labels = torch.full((1, 10), -100, dtype=torch.int64)
+    labels[0, 3:6] = 32100
+    with pytest.raises(RuntimeError, match="is invalid for input of size"):
+        arch.gather_hand_traj_states(torch.zeros(1, 10, 8, device=DEV), labels.to(DEV))
+
+
+def test_gather_backward_and_step():
+    hidden = synth.gen("gh", (3, 50, 4096), 1.0, 7).to(DEV).requires_grad_(True)
+    labels = torch.full((3, 50), -100, dtype=torch.int64)
+    labels[0, 40:44] = 32100
+    labels[2, [5, 6, 30, 49]] = 32100
+    out, valid, rows, counts = ops.hand_gather(hidden, labels.to(DEV), 32100)
+    dout = synth.gen("gdout", tuple(out.shape), 1.0, 7)
+    out.backward(dout.to(DEV))
+    ro, rv, rr = restate.gather_hand_traj(hidden.detach().cpu(), labels)
+    assert torch.equal(out.detach().cpu(), ro) and torch.equal(rows.cpu(), rr)
+    assert torch.equal(hidden.grad.cpu(), restate.gather_hand_traj_backward(dout, rr, 50))
+    last = synth.gen("glast", (2, 4096), 1.0, 8)
+    assert torch.equal(ops.hand_gather_step(last.to(DEV)).cpu(), restate.gather_hand_traj_step(last))
+
+
+# ------------------------------------------------------------------ splice
+class _Inner(torch.nn.Module):
+    def __init__(self, tower, proj, emb):
+        super().__init__()
+        self.vision_tower, self.mm_projector, self.embed_tokens = tower, proj, emb
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+
+def _host(mixin, tower, proj, emb, config, B):
+    class Host(torch.nn.Module, mixin):
+        def __init__(self):
+            super().__init__()
+            self.model = _Inner(tower, proj, emb)
+            self.config = config
+            self.token_dim, self.B = proj.out_features, B
+
+        def get_model(self):
+            return self.model
+    return Host().to(DEV)
+
+
+@pytest.fixture(scope="module")
+def small():
+    sd, proj, emb = small_parts()
+    return sd, proj, emb
+
+
+def _small_visual(small, px, mode="temporal_spatial_pool"):
+    sd, proj, _ = small
+    return restate.pipeline(px, sd, proj.weight.data, proj.bias.data, mode, select_layer=-2, cfg=SMALL)[0]
+
+
+def _splice_cuda(variant, ids, mask, labels, vis, table, fh=None, is_eval=False, static=False):
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=table.to(DEV))),
+        config=types.SimpleNamespace(hvlm_static_splice=static))
+    dv = lambda x: None if x is None else x.to(DEV)
+    return arch.splice_tokens(host, variant, dv(ids), dv(mask), dv(labels), dv(vis), None, dv(fh), is_eval)
+
+
+@pytest.mark.parametrize("name,is_eval", [
+    ("splice_hvlm_train_b3", False), ("splice_hvlm_train_padded", False), ("splice_hvlm_2hand", False),
+    ("splice_hvlm_0hand", False), ("splice_hvlm_ragged", False), ("splice_hvlm_eval_hands", True),
+    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False)])
+def test_splice_handsonvlm_vs_reference_fixture(golden, small, name, is_eval):
+    g = golden(name)
+    ids = T(g["ids"])
+    px = synth.pixels((ids.shape[0], int(g["t"]), 3, 224, 224), seed=int(g["px_seed"]))
+    vis = _small_visual(small, px)                       # visual tokens from the oracle: isolates the splice
+    mask = T(g["in_mask"]) if "in_mask" in g.files else None
+    labels = T(g["in_labels"]) if "in_labels" in g.files else None
+    fh = T(g["future_hands"]) if "future_hands" in g.files else None
+    m2, e2, l2 = _splice_cuda(L.SPLICE_HANDSONVLM, ids, mask, labels, vis, small[2].weight.data, fh, is_eval)
+    ge = T(g["embeds"])
+    assert e2.shape == ge.shape
+    assert relmax(e2, ge) <= 2e-5
+    # copied rows are bit-exact against the oracle's spliced tensor
+    rm, re_, rl = restate.splice(ids, mask, labels, vis, small[2].weight.data, "handsonvlm", future_hands=fh,
+                                 is_evaluate=is_eval)
+    diff_rows = (e2.cpu() != re_).any(-1).sum().item()
+    assert diff_rows <= 4 * ids.shape[0]                 # only <hand_traj> rows carry fp adds
+    if "labels" in g.files:
+        assert torch.equal(l2.cpu(), T(g["labels"]))
+    else:
+        assert l2 is None
+    if "mask" in g.files:
+        assert str(m2.dtype) == str(g["mask_dtype"]) and torch.equal(m2.cpu(), T(g["mask"]))
+    else:
+        assert m2 is None
+
+
+@pytest.mark.parametrize("name,pxshape,pxseed,cfg", [
+    ("splice_llava_cfg1", (1, 3, 224, 224), 12, "image"), ("splice_llava_ragged", (2, 3, 224, 224), 13, "image"),
+    ("splice_llava_two_images", (2, 3, 224, 224), 14, "image"), ("splice_llava_video", (1, 4, 3, 224, 224), 15, "video")])
+def test_splice_llava_vs_reference_fixture(golden, small, name, pxshape, pxseed, cfg):
+    g = golden(name)
+    sd, proj, emb = small
+    px = synth.pixels(pxshape, seed=pxseed)
+    if cfg == "image":
+        vis = restate.project(restate.tower_forward(px, sd, -2, SMALL), proj.weight.data, proj.bias.data)
+    else:
+        vis = _small_visual(small, px)
+    m2, e2, l2 = _splice_cuda(L.SPLICE_LLAVA, T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, emb.weight.data)
+    assert torch.equal(e2.cpu(), T(g["embeds"]))         # pure copies: bit-exact
+    assert torch.equal(l2.cpu(), T(g["labels"]))
+    assert m2.dtype == torch.bool and torch.equal(m2.cpu(), T(g["mask"]))
+
+
+def test_splice_static_mode_no_sync_and_status_flag():
+    D = 256
+    table = synth.embed_table(D)
+    vis = synth.gen("vis", (2, 356, D), 1.0, 5)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=2, seed=3)
+    m2, e2, l2 = _splice_cuda(L.SPLICE_HANDSONVLM, ids, mask, labels, vis, table, fh, static=True)
+    rm, re_, rl = restate.splice(ids, mask, labels, vis, table, "handsonvlm", future_hands=fh)
+    assert torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm) and relmax(e2, re_) <= 2e-5
+    assert l2[0, 411:415].tolist() == [32100] * 4 and e2.shape == (2, 417, D)
+    # bad token id -> IndexError like nn.Embedding
+    bad = ids.clone()
+    bad[0, 3] = 40000
+    with pytest.raises(IndexError):
+        _splice_cuda(L.SPLICE_HANDSONVLM, bad, mask, labels, vis, table, fh)
+    # more hand tokens than future_hands points in eval mode -> AssertionError like the reference
+    with pytest.raises(AssertionError):
+        _splice_cuda(L.SPLICE_HANDSONVLM, ids, mask, labels, vis, table, fh[:, :, :3], is_eval=True)
+
+
+def test_splice_backward_matches_oracle():
+    D, B = 128, 2
+    table = synth.embed_table(D).to(DEV).requires_grad_(True)
+    vis = synth.gen("vis", (B, 356, D), 1.0, 5).to(DEV).requires_grad_(True)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=B, seed=4)
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=table)),
+        config=types.SimpleNamespace())
+    m2, e2, l2 = arch.splice_tokens(host, L.SPLICE_HANDSONVLM, ids.to(DEV), mask.to(DEV), labels.to(DEV), vis, None,
+                                    fh.to(DEV), False)
+    de = synth.gen("de", tuple(e2.shape), 1.0, 6)
+    e2.backward(de.to(DEV))
+    dv, dt = restate.splice_backward(de, ids, 356, B, table.shape[0])
+    assert torch.equal(vis.grad.cpu(), dv)
+    assert relmax(table.grad, dt) <= 1e-6                 # atomics: order-dependent fp32 sums
+
+
+# ------------------------------------------------------------------ ViT stages
+def test_qkv_and_attention_stage():
+    F = 3
+    y = synth.gen("attn.y", (F * 257, 1024), 1.0, 1).to(torch.bfloat16)
+    w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
+    b = synth.gen("attn.b", (3072,), 0.1, 1)
+    q, k, vt = ops.vit_qkv(y.to(DEV), w.to(DEV), b.to(DEV), F)
+    ref = (y.float() @ w.float().t() + b).reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)
+    assert relmax(q, ref[0]) <= 5e-3 and relmax(k, ref[1]) <= 5e-3
+    assert relmax(vt[..., :257], ref[2].transpose(-1, -2)) <= 5e-3
+    for scale in (0.125, 1.0):
+        qs = (q.float() * scale).to(torch.bfloat16)
+        o = ops.vit_attention(qs, k, vt)
+        s = qs.float().cpu() @ k.float().cpu().transpose(-1, -2)
+        oref = (torch.softmax(s, -1) @ vt[..., :257].float().cpu().transpose(-1, -2)).permute(0, 2, 1, 3).reshape(F * 257, 1024)
+        assert relmax(o, oref) <= 8e-3
+
+
+@pytest.fixture(scope="module")
+def tower23():
+    towers = {}
+
+    def get(profile):
+        if profile not in towers:
+            sd = synth.clip_state_dict(synth.VIT_L14, 0, profile, n_layers=23)
+            tw = CLIPVisionTower("synthetic", types.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+            tw.load_model(sd)
+            towers[profile] = (tw.to(DEV), sd)
+        return towers[profile]
+    return get
+
+
+@pytest.mark.parametrize("profile", ["hf", "strong"])
+def test_vit_l14_vs_hf_reference_fixture(golden, tower23, profile):
+    """CUDA tower (bf16 operands, fp32 residual) vs HF CLIPVisionModel fp32 run through the reference's
+    CLIPVisionTower.forward (fixture)."""
+    g = golden(f"vit_l14_{profile}")
+    tw, sd = tower23(profile)
+    px = synth.pixels((2, 3, 224, 224), seed=3)
+    feats = tw(px.to(DEV))
+    assert feats.shape == (2, 256, 1024) and feats.dtype == torch.float32
+    sub = T(g["sub"])
+    err = float((feats[:, ::8, ::4].cpu() - sub).abs().max() / float(g["absmax"]))
+    assert err <= TOL_BF16, err
+    assert relmax(feats.norm(dim=-1), T(g["norms"])) <= TOL_BF16
+    # list input -> list output, per image (clip_encoder.py:41-46), output dtype follows the image dtype
+    lst = tw([px[0].to(DEV).half(), px[1].to(DEV).half()])
+    assert isinstance(lst, list) and lst[0].shape == (1, 256, 1024) and lst[0].dtype == torch.float16
+
+
+def test_vit_l14_tracks_bf16_operand_oracle(tower23):
+    """Tight check against the oracle run with bf16-rounded GEMM operands (same numeric regime): catches
+    structural bugs that the 1e-2 fp32 tolerance could hide."""
+    tw, sd = tower23("strong")
+    px = synth.pixels((1, 3, 224, 224), seed=5)
+    hid = tw.forward_hidden(px.to(DEV))
+    emu = restate.vit_hidden(px, sd, 23, emulate="bf16")
+    assert relmax(hid, emu) <= 4e-3
+
+
+def test_tower_rejects_wrong_image_size(tower23):
+    tw, _ = tower23("hf")
+    with pytest.raises(ValueError):
+        tw(torch.zeros(1, 3, 112, 112, device=DEV))
+
+
+# ------------------------------------------------------------------ whole path through the drop-in interface
+def test_handsonvlm_path_end_to_end(tower23):
+    """SURVEY 8d config 2 at reduced frame count: pixels -> ViT -> pool -> projector(4096) -> splice -> gather,
+    through the reference's method signatures, against the fp32 oracle."""
+    tw, sd = tower23("hf")
+    D, t, B = 4096, 6, 2
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    cfg = types.SimpleNamespace(fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool",
+                                mm_hidden_size=1024, input_type="video")
+    host = _host(arch.HandsOnVLMMetaForCausalLM, tw, proj.to(torch.bfloat16), emb.to(torch.bfloat16), cfg, B)
+    px = synth.pixels((B, t, 3, 224, 224), seed=9)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=B, seed=9)
+    with torch.no_grad():
+        r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV),
+                                                      px.to(DEV).to(torch.bfloat16), future_hands=fh.to(DEV),
+                                                      future_valid=fv.to(DEV), is_evaluate=False)
+    assert r[0] is None and r[2] is None
+    m2, e2, l2 = r[1], r[3], r[4]
+    vis, _ = restate.pipeline(px.to(torch.bfloat16).float(), sd, ps["mm_projector.weight"], ps["mm_projector.bias"])
+    table = synth.embed_table(D).to(torch.bfloat16).float()
+    rm, re_, rl = restate.splice(ids, mask, labels, vis, table, "handsonvlm", future_hands=fh)
+    assert e2.shape == (B, ids.shape[1] + 6 + 256 - 1, D) and e2.dtype == torch.bfloat16
+    assert torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm)
+    assert relmax(e2, re_) <= TOL_BF16
+    hidden = synth.gen("e2e.hidden", tuple(e2.shape), 1.0, 9).to(torch.bfloat16)
+    gout, valid = host.gather_hand_traj_states(hidden.to(DEV), l2, future_valid=fv.to(DEV))
+    ro, rv, _ = restate.gather_hand_traj(hidden, rl)
+    assert torch.equal(gout.cpu(), ro) and torch.equal(valid.cpu(), rv)
+    assert int(host.last_visual_token_index) == 35 + 262
+
+
+def test_llava_config1_single_image_fp32(tower23):
+    """BASELINE config 1: single 224x224 image, fp32, 256 tokens -> projector 4096 -> LLaVA splice."""
+    tw, sd = tower23("hf")
+    D = 4096
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    host = _host(arch.LitaMetaForCausalLM, tw, proj, emb, types.SimpleNamespace(input_type="image"), 1)
+    px = synth.pixels((1, 3, 224, 224), seed=12)
+    ids, mask, labels = synth.prompt_llava(seed=31)
+    with torch.no_grad():
+        r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px.to(DEV))
+    m2, e2, l2 = r[1], r[3], r[4]
+    vis = restate.project(restate.tower_forward(px, sd, -2), ps["mm_projector.weight"], ps["mm_projector.bias"])
+    rm, re_, rl = restate.splice(ids, mask, labels, vis, synth.embed_table(D), "llava")
+    assert e2.shape == (1, 311, D) and e2.dtype == torch.float32
+    assert torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm)
+    assert (l2[0, 35:291] == -100).all()
+    assert relmax(e2[0, 35:291], re_[0, 35:291]) <= TOL_BF16
+    assert torch.equal(e2[0, :35].cpu(), re_[0, :35])
+    # T == 1 early-out (llava_arch.py:117-120)
+    pkv = [[torch.zeros(1, 2, 9, 4, device=DEV), torch.zeros(1, 2, 9, 4, device=DEV)]]
+    r = host.prepare_inputs_labels_for_multimodal(torch.tensor([[5]], device=DEV), torch.ones(1, 1, dtype=torch.bool, device=DEV),
+                                                  pkv, None, px.to(DEV))
+    assert r[3] is None and r[1].shape == (1, 10)
+
+
+def test_lita_videos_to_tokens_archs(tower23):
+    tw, sd = tower23("hf")
+    D = 256
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    px = synth.pixels((1, 5, 3, 224, 224), seed=7)
+    feats = restate.tower_forward(px[0], sd, -2)
+    tok = restate.project(feats, ps["mm_projector.weight"], ps["mm_projector.bias"]).reshape(1, 5, 256, D)
+    for arch_name in ("all", "temporal", "spatial", "temporal_spatial", "temporal_spatial_pool", "spatial_pool"):
+        host = _host(arch.LitaMetaForCausalLM, tw, proj, torch.nn.Embedding(4, D),
+                     types.SimpleNamespace(input_type="video", video_arch=arch_name), 1)
+        with torch.no_grad():
+            out = host.visual_to_tokens(px.to(DEV))
+        ref = restate.pool_tokens(tok, arch_name)
+        assert out.shape == ref.shape and relmax(out, ref) <= TOL_BF16
+    with pytest.raises(ValueError):
+        _host(arch.LitaMetaForCausalLM, tw, proj, torch.nn.Embedding(4, D),
+              types.SimpleNamespace(input_type="video", video_arch="nope"), 1).visual_to_tokens(px.to(DEV))
+
+
+def test_training_shaped_backward(tower23):
+    """fwd + bwd through pooling / projector / splice / gather with upstream grads; projector and visual
+    gradients against the fp32 oracle (SURVEY 8d config 5 at reduced size)."""
+    tw, sd = tower23("hf")
+    D, t, B = 512, 4, 2
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    cfg = types.SimpleNamespace(fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool",
+                                mm_hidden_size=1024, input_type="video")
+    host = _host(arch.HandsOnVLMMetaForCausalLM, tw, proj, emb, cfg, B)
+    px = synth.pixels((B, t, 3, 224, 224), seed=19)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=B, seed=19)
+    r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px.to(DEV),
+                                                  future_hands=fh.to(DEV), future_valid=fv.to(DEV), is_evaluate=False)
+    e2, l2 = r[3], r[4]
+    gout, _ = host.gather_hand_traj_states(e2, l2)          # use the embeddings as stand-in hidden states
+    de = synth.gen("tr.de", tuple(e2.shape), 1.0, 19)
+    dg = synth.gen("tr.dg", tuple(gout.shape), 1.0, 19)
+    ((e2 * de.to(DEV)).sum() + (gout * dg.to(DEV)).sum()).backward()
+    # oracle: grads wrt spliced embeddings = de + scatter(dg); -> visual rows -> pooled-token grads -> dW, db
+    _, _, rows = restate.gather_hand_traj(torch.zeros(B, e2.shape[1], D), l2.cpu())
+    d_emb = de + restate.gather_hand_traj_backward(dg, rows, e2.shape[1])
+    d_vis, d_tab = restate.splice_backward(d_emb, ids, t + 256, B, synth.VOCAB)
+    feats = restate.tower_forward(px.reshape(B * t, 3, 224, 224), sd, -2).reshape(B, t, 256, 1024)
+    pooled = restate.pool_tokens(feats, "temporal_spatial_pool")
+    dW, db = restate.projector_grads(pooled, d_vis)
+    pw, pb = host.model.mm_projector.weight, host.model.mm_projector.bias
+    assert relmax(pw.grad, dW) <= TOL_BF16 and relmax(pb.grad, db) <= 1e-4
+    assert relmax(host.model.embed_tokens.weight.grad, d_tab) <= 1e-5
