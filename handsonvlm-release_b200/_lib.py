@@ -21,6 +21,8 @@ SPLICE_LLAVA, SPLICE_HANDSONVLM = 0, 1
 EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PLAN_ERR_LEN_OVERFLOW, PLAN_ERR_IMG_OVERFLOW, PLAN_ERR_HAND_COUNT, PLAN_ERR_BAD_ID, PLAN_NOT_UNIFORM = 1, 2, 4, 8, 16
 VIT_MAX_LAYERS = 24
+STAGES = ["im2col", "patch_gemm", "layernorm", "qkv_gemm", "attention", "outproj_gemm", "fc1_gemm", "fc2_gemm", "pool",
+          "gemm", "splice", "gather", "other"]
 
 p = C.c_void_p
 i32, i64, f32, sz = C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -48,8 +50,7 @@ SIGNATURES = {
     "hvlm_vit_l14_fwd": (i32, [p, i32, p, i32, i32, p, p, sz, p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
-    "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, p, p, i32, p]),
-    "hvlm_vit_attention": (i32, [p, p, p, p, i32, p]),
+    "hvlm_vit_attention": (i32, [p, p, i32, p]),
     "hvlm_pool_out_tokens": (i32, [i32, i32]),
     "hvlm_pool_slowfast_fwd": (i32, [p, i32, i64, p, i32, i32, i32, i32, i32, p]),
     "hvlm_pool_slowfast_bwd": (i32, [p, i32, p, i32, i32, i32, i32, i32, p]),
@@ -62,6 +63,9 @@ SIGNATURES = {
     "hvlm_hand_gather_step": (i32, [p, i32, i32, i32, p, p]),
     "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
     "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
+    "hvlm_launch_count": (C.c_uint64, []),
+    "hvlm_profile_enable": (i32, [i32]),
+    "hvlm_profile_collect": (i32, [C.POINTER(f32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -2,8 +2,10 @@
 // 257 tokens x 64 dims, no mask, no dropout (HF CLIPAttention in eval; q already carries the 64^-1/2 scale).
 //
 // One persistent CTA per SM walks (frame, head) items.  Per item:
-//   TMA   : Q [257x64] -> 3 row tiles of 128 (rows >= 257 zero-filled), K -> [272x64], V^T -> 5 key blocks
-//           [64 d x 64 keys] (keys >= 257 zero-filled), all SWIZZLE_128B K-major operand tiles
+//   TMA   : Q, K, V head slices [257x64] straight out of the QKV GEMM's [M,3072] output through ONE 4-D tensor
+//           map (d, token, column block, frame): Q -> 3 row tiles of 128, K and V -> [272x64]; rows >= 257 are
+//           zero-filled by the TMA unit.  Q/K/P are K-major SWIZZLE_128B operands; V is consumed as an
+//           MN-major B operand (no transpose anywhere).
 //   MMA 1 : S[128 x 272] = Q_tile K^T     tcgen05.mma M=128, N=256 (+ N=16 for keys 256..271), K=16 x 4
 //           fp32 accumulator in TMEM columns [0,272)
 //   softmax (4 warps, one row per thread): two passes over the TMEM row (max, then exp/sum in fp32);
@@ -24,17 +26,16 @@ constexpr int kSK = 272;                   // keys padded to a multiple of 16
 constexpr int kQTile = 128 * 64 * 2;       // 16384
 constexpr int kQBytes = 3 * kQTile;        // 49152
 constexpr int kKBytes = kSK * 64 * 2;      // 34816
-constexpr int kVBlock = 64 * 64 * 2;       // 8192
-constexpr int kVBytes = 5 * kVBlock;       // 40960
+constexpr int kVBytes = kSK * 64 * 2;      // 34816
 constexpr int kPBlock = 128 * 64 * 2;      // 16384
 constexpr int kPBytes = 5 * kPBlock;       // 81920
 constexpr int kAttnSmem = kQBytes + kKBytes + kVBytes + kPBytes + 1024 + 128;
 constexpr int kOCol = 320;                 // TMEM column of the O accumulator
 constexpr uint32_t kQKTx = kQBytes + 2 * kQTile + 16 * 128;   // Q (3 boxes) + K (2 boxes of 128 rows + 16 rows)
+constexpr uint32_t kVTx = 2 * kQTile + 16 * 128;              // V (2 boxes of 128 rows + 16 rows)
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
-attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                    const __grid_constant__ CUtensorMap tm_ktail, const __grid_constant__ CUtensorMap tm_vt,
+attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail,
                     __nv_bfloat16* __restrict__ out, int n_items) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -56,10 +57,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            tma_prefetch_desc(&tm_q);
-            tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_ktail);
-            tma_prefetch_desc(&tm_vt);
+            tma_prefetch_desc(&tm_qkv);
+            tma_prefetch_desc(&tm_tail);
             mbar_init(qk_full, 1);
             mbar_init(v_full, 1);
             mbar_init(s_full, 1);
@@ -79,25 +78,29 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (lane == 0) {
             constexpr uint32_t idesc_s256 = umma_idesc_bf16(128, 256);
             constexpr uint32_t idesc_s16 = umma_idesc_bf16(128, 16);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, /*b_mn_major=*/1);
             const uint64_t dQ = umma_desc_k_sw128(smem_u32(sQ));
             const uint64_t dK = umma_desc_k_sw128(smem_u32(sK));
             const uint64_t dV = umma_desc_k_sw128(smem_u32(sV));
             const uint64_t dP = umma_desc_k_sw128(smem_u32(sP));
 
+            // item = frame*16 + head; column blocks of the [M,3072] QKV matrix: q -> head, k -> 16+head, v -> 32+head
             auto load_qk = [&](int item) {
+                const int f = item >> 4, h = item & 15;
                 mbar_arrive_expect_tx(qk_full, kQKTx);
-                tma_load_3d(sQ, &tm_q, qk_full, 0, 0, item);
-                tma_load_3d(sQ + kQTile, &tm_q, qk_full, 0, 128, item);
-                tma_load_3d(sQ + 2 * kQTile, &tm_q, qk_full, 0, 256, item);
-                tma_load_3d(sK, &tm_k, qk_full, 0, 0, item);
-                tma_load_3d(sK + kQTile, &tm_k, qk_full, 0, 128, item);
-                tma_load_3d(sK + 2 * kQTile, &tm_ktail, qk_full, 0, 256, item);
+                tma_load_4d(sQ, &tm_qkv, qk_full, 0, 0, h, f);
+                tma_load_4d(sQ + kQTile, &tm_qkv, qk_full, 0, 128, h, f);
+                tma_load_4d(sQ + 2 * kQTile, &tm_qkv, qk_full, 0, 256, h, f);
+                tma_load_4d(sK, &tm_qkv, qk_full, 0, 0, 16 + h, f);
+                tma_load_4d(sK + kQTile, &tm_qkv, qk_full, 0, 128, 16 + h, f);
+                tma_load_4d(sK + 2 * kQTile, &tm_tail, qk_full, 0, 256, 16 + h, f);
             };
             auto load_v = [&](int item) {
-                mbar_arrive_expect_tx(v_full, kVBytes);
-#pragma unroll
-                for (int kb = 0; kb < 5; ++kb) tma_load_3d(sV + kb * kVBlock, &tm_vt, v_full, kb * 64, 0, item);
+                const int f = item >> 4, h = item & 15;
+                mbar_arrive_expect_tx(v_full, kVTx);
+                tma_load_4d(sV, &tm_qkv, v_full, 0, 0, 32 + h, f);
+                tma_load_4d(sV + kQTile, &tm_qkv, v_full, 0, 128, 32 + h, f);
+                tma_load_4d(sV + 2 * kQTile, &tm_tail, v_full, 0, 256, 32 + h, f);
             };
             auto issue_s = [&](int tile) {
                 // S = Q_tile K^T : 4 k-steps over the 64 head dims
@@ -131,12 +134,14 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     mbar_wait(p_full, n3 & 1);
                     if (tile == 0) mbar_wait(v_full, it & 1);
                     tc_fence_after();
-                    // O = P V : 17 k-steps of 16 keys (272 = keys padded; P and V^T pads are zero)
+                    // O = P V : 17 k-steps of 16 keys (272 = keys padded; P and V pad rows are zero).
+                    // A = P (K-major: +32 B per step inside a 64-key block); B = V rows [key, d] as an MN-major
+                    // operand: 16 keys = 16 rows of 128 B = +2048 B per step.
 #pragma unroll
                     for (int kk = 0; kk < 17; ++kk) {
                         const uint32_t blk = kk >> 2, sub = kk & 3;
                         umma_bf16_ss(tmem_base + kOCol, dP + static_cast<uint64_t>((blk * kPBlock) >> 4) + 2 * sub,
-                                     dV + static_cast<uint64_t>((blk * kVBlock) >> 4) + 2 * sub, idesc_o, kk > 0);
+                                     dV + static_cast<uint64_t>((kk * 2048) >> 4), idesc_o, kk > 0);
                     }
                     umma_commit(o_full);
                     if (tile < 2) issue_s(tile + 1);
@@ -262,26 +267,18 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_attention(const void* q, const void* k, const void* vt, void* out, int n_frames, cudaStream_t s) {
+int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s) {
     const int n_items = n_frames * HVLM_VIT_HEADS;
-    CUtensorMap tq, tk, tkt, tv;
+    CUtensorMap tq, tt;
     {
-        uint64_t dims[3] = {64, static_cast<uint64_t>(kS), static_cast<uint64_t>(n_items)};
-        uint64_t str[2] = {128, static_cast<uint64_t>(kS) * 128};
-        uint32_t box[3] = {64, 128, 1};
-        uint32_t box_tail[3] = {64, 16, 1};
-        int rc = make_tmap_bf16(&tq, q, 3, dims, str, box);
+        // qkv [n_frames*257, 3072] bf16 viewed as (d:64, token:257, column block:48, frame)
+        uint64_t dims[4] = {64, static_cast<uint64_t>(kS), 48, static_cast<uint64_t>(n_frames)};
+        uint64_t str[3] = {3072 * 2, 128, static_cast<uint64_t>(kS) * 3072 * 2};
+        uint32_t box[4] = {64, 128, 1, 1};
+        uint32_t box_tail[4] = {64, 16, 1, 1};
+        int rc = make_tmap_bf16(&tq, qkv, 4, dims, str, box);
         if (rc) return rc;
-        rc = make_tmap_bf16(&tk, k, 3, dims, str, box);
-        if (rc) return rc;
-        rc = make_tmap_bf16(&tkt, k, 3, dims, str, box_tail);
-        if (rc) return rc;
-    }
-    {
-        uint64_t dims[3] = {static_cast<uint64_t>(kS), 64, static_cast<uint64_t>(n_items)};
-        uint64_t str[2] = {HVLM_VT_STRIDE * 2, 64ull * HVLM_VT_STRIDE * 2};
-        uint32_t box[3] = {64, 64, 1};
-        int rc = make_tmap_bf16(&tv, vt, 3, dims, str, box);
+        rc = make_tmap_bf16(&tt, qkv, 4, dims, str, box_tail);
         if (rc) return rc;
     }
     static bool attr_set[64] = {false};
@@ -293,15 +290,16 @@ int launch_attention(const void* q, const void* k, const void* vt, void* out, in
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int grid = n_items < num_sms() ? n_items : num_sms();
-    attn_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tk, tkt, tv, static_cast<__nv_bfloat16*>(out), n_items);
+    attn_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmem, s>>>(tq, tt, static_cast<__nv_bfloat16*>(out), n_items);
     return check_last("attention");
 }
 
 }  // namespace hvlm
 
-extern "C" int hvlm_vit_attention(const void* q, const void* k, const void* vt, void* out, int n_frames, void* stream) {
+extern "C" int hvlm_vit_attention(const void* qkv, void* out, int n_frames, void* stream) {
     using namespace hvlm;
-    if (!q || !k || !vt || !out || n_frames <= 0) return HVLM_ERR_BAD_ARG;
-    if (!aligned16(q) || !aligned16(k) || !aligned16(vt) || !aligned16(out)) return HVLM_ERR_ALIGN;
-    return launch_attention(q, k, vt, out, n_frames, static_cast<cudaStream_t>(stream));
+    if (!qkv || !out || n_frames <= 0) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(qkv) || !aligned16(out)) return HVLM_ERR_ALIGN;
+    StageTimer st(HVLM_STAGE_ATTENTION, static_cast<cudaStream_t>(stream));
+    return launch_attention(qkv, out, n_frames, static_cast<cudaStream_t>(stream));
 }

@@ -6,7 +6,7 @@
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), fp32 accumulators in
 //     TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   * 4 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns), apply the epilogue
-//     (bias / quick-GELU / fp32 residual / ViT QKV head scatter / patch-embed + position embedding)
+//     (bias / quick-GELU / fp32 residual via TMA reduce-add / patch-embed + position embedding)
 //     and store 128-bit vectors
 //   * persistent: grid = min(tiles, #SM); tiles are walked N-fastest so concurrently running CTAs share
 //     A rows and the (small, L2-resident) weight matrix
@@ -36,8 +36,8 @@ static void load_encode() {
     }
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box) {
+static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
     std::call_once(g_encode_once, load_encode);
     if (!g_encode) return HVLM_ERR_CUDA;
     cuuint64_t gdim[5];
@@ -50,11 +50,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
         es[i] = 1;
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
-    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+    CUresult r = g_encode(out, dt, static_cast<cuuint32_t>(rank),
                           const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? HVLM_OK : HVLM_ERR_CUDA;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 int num_sms() {
@@ -69,7 +78,10 @@ int num_sms() {
     return cached[dev];
 }
 
-int check_last(const char*) { return cudaGetLastError() == cudaSuccess ? HVLM_OK : HVLM_ERR_CUDA; }
+int check_last(const char*) {
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? HVLM_OK : HVLM_ERR_CUDA;
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernel
@@ -85,12 +97,48 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = 2 * BN;   // double-buffered accumulator: 256 or 512 columns
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kStoreBuf = BM * 128;   // one staging unit: 128 rows x 128 B (SWIZZLE_128B box)
+    static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBuf + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float quick_gelu(float x) {
-    // x * sigmoid(1.702 x)  (HF QuickGELUActivation)
-    return x / (1.0f + __expf(-1.702f * x));
+    // x * sigmoid(1.702 x)  (HF QuickGELUActivation); sigmoid(z) = 0.5 tanh(z/2) + 0.5 -> one MUFU op, no divide
+    const float hx = 0.5f * x;
+    return fmaf(hx, tanh_approx(0.851f * x), hx);
+}
+
+template <int EPI>
+__host__ __device__ constexpr bool epi_is_staged() {
+    return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_F32 || EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32 ||
+           EPI == EPI_RESID_F32;
+}
+template <int EPI>
+__host__ __device__ constexpr bool epi_out_f32() {
+    return EPI == EPI_BIAS_F32 || EPI == EPI_GELU_F32 || EPI == EPI_RESID_F32;
+}
+
+// acc (32 fp32 columns of this thread's row) -> +bias -> (quick-GELU) -> v
+template <int EPI>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], const float* __restrict__ bias, int n0,
+                                              float (&v)[32]) {
+    if (bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    }
+    if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    }
 }
 
 template <int EPI>
@@ -119,7 +167,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
     }
-    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_RESID_BF16) {
+    if constexpr (EPI == EPI_RESID_F32) {
         const float4* r4 = reinterpret_cast<const float4*>(ep.resid + static_cast<size_t>(m) * N + n0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -131,7 +179,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m,
         }
     }
 
-    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_RESID_BF16) {
+    if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16) {
         uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + static_cast<size_t>(m) * N + n0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -146,33 +194,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m,
         float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + static_cast<size_t>(m) * N + n0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else if constexpr (EPI == EPI_QKV) {
-        // n0 in [0,3072): which = q|k|v, head, d0 in {0,32}; row m = frame*257 + tok
-        const int which = n0 >> 10;
-        const int head = (n0 & 1023) >> 6;
-        const int d0 = n0 & 63;
-        const int f = m / HVLM_VIT_TOKENS;
-        const int tok = m - f * HVLM_VIT_TOKENS;
-        const size_t fh = static_cast<size_t>(f) * HVLM_VIT_HEADS + head;
-        if (which < 2) {
-            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(which == 0 ? ep.q : ep.k);
-            uint4* o = reinterpret_cast<uint4*>(base + (fh * HVLM_VIT_TOKENS + tok) * 64 + d0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 w;
-                w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                o[j] = w;
-            }
-        } else {
-            // V is stored transposed ([d, key]) so that it is a K-major B operand for the P*V MMA;
-            // consecutive lanes hold consecutive tokens -> 2-byte stores coalesce across the warp.
-            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(ep.vt) + (fh * 64 + d0) * HVLM_VT_STRIDE + tok;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) base[static_cast<size_t>(j) * HVLM_VT_STRIDE] = __float2bfloat16_rn(v[j]);
-        }
     } else if constexpr (EPI == EPI_PATCH) {
         const int f = m >> 8;
         const int p = m & 255;
@@ -190,8 +211,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m,
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, int M,
-                    int N, int K, EpiArgs ep) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiArgs ep) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -200,7 +221,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_c = smem + kStages * Cfg::kStageBytes;   // 2 staging units for the TMA-store epilogue
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * Cfg::kStoreBuf);
     uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
     uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA
     uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue
@@ -217,6 +239,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        if constexpr (epi_is_staged<EPI>()) tma_prefetch_desc(&tma_c);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -294,25 +317,96 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / num_n;
-            const int n_blk = tile - m_blk * num_n;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const int m = m_blk * BM + q * 32 + lane;
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+        if constexpr (epi_is_staged<EPI>()) {
+            // TMEM -> registers -> (bias / GELU) -> swizzled smem staging unit -> TMA store (or TMA reduce-add
+            // into the fp32 residual stream).  Global traffic is fully coalesced and asynchronous; the M tail
+            // is clipped by the TMA unit.
+            constexpr bool kF32 = epi_out_f32<EPI>();
+            constexpr int kUnitCols = kF32 ? 32 : 64;            // 128 bytes per row either way
+            constexpr int kUnits = BN / kUnitCols;
+            const int row = q * 32 + lane;
+            const int sw = row & 7;
+            const bool issuer = (warp == 2 && lane == 0);
+            uint32_t ucount = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n;
+                const int n_blk = tile - m_blk * num_n;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(t_row + static_cast<uint32_t>(c * 32), r);
-                tmem_ld_wait();
-                epilogue_chunk<EPI>(r, m, n_blk * BN + c * 32, M, N, ep);
+                for (int u = 0; u < kUnits; ++u, ++ucount) {
+                    uint8_t* buf = smem_c + (ucount & 1u) * Cfg::kStoreBuf;
+                    uint8_t* brow = buf + row * 128;
+                    if (issuer) bulk_wait_read<1>();              // the store that last used this buffer is done
+                    named_bar_sync(1, 128);
+                    const int n0 = n_blk * BN + u * kUnitCols;
+#pragma unroll
+                    for (int h = 0; h < kUnitCols / 32; ++h) {
+                        uint32_t r[32];
+                        tmem_ld32(t_row + static_cast<uint32_t>(u * kUnitCols + h * 32), r);
+                        tmem_ld_wait();
+                        float v[32];
+                        epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
+                        if constexpr (kF32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(brow + ((j ^ sw) << 4)) =
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 w;
+                                w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                                w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                                w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                                w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                                *reinterpret_cast<uint4*>(brow + (((h * 4 + j) ^ sw) << 4)) = w;
+                            }
+                        }
+                    }
+                    if (u == kUnits - 1) {
+                        // last TMEM read of this accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(&tempty_bar[acc]);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (issuer) {
+                        if constexpr (EPI == EPI_RESID_F32)
+                            tma_reduce_add_2d(&tma_c, buf, n0, m_blk * BM);
+                        else
+                            tma_store_2d(&tma_c, buf, n0, m_blk * BM);
+                        bulk_commit();
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
             }
-            tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) {
-                acc = 0;
-                acc_phase ^= 1u;
+            if (issuer) bulk_wait<0>();
+        } else {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n;
+                const int n_blk = tile - m_blk * num_n;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const int m = m_blk * BM + q * 32 + lane;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + static_cast<uint32_t>(c * 32), r);
+                    tmem_ld_wait();
+                    epilogue_chunk<EPI>(r, m, n_blk * BN + c * 32, M, N, ep);
+                }
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
             }
         }
     }
@@ -343,6 +437,22 @@ static int launch_one(const void* A, const void* B, int M, int N, int K, const E
         int rc = make_tmap_bf16(&tb, B, 2, dims, str, box);
         if (rc) return rc;
     }
+    CUtensorMap tc = tb;   // unused by the direct-store epilogues
+    if constexpr (epi_is_staged<EPI>()) {
+        if (!ep.out || !aligned16(ep.out)) return HVLM_ERR_ALIGN;
+        uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+        int rc;
+        if constexpr (epi_out_f32<EPI>()) {
+            uint64_t str[1] = {static_cast<uint64_t>(N) * 4};
+            uint32_t box[2] = {32, BM};
+            rc = make_tmap_f32(&tc, ep.out, 2, dims, str, box);
+        } else {
+            uint64_t str[1] = {static_cast<uint64_t>(N) * 2};
+            uint32_t box[2] = {64, BM};
+            rc = make_tmap_bf16(&tc, ep.out, 2, dims, str, box);
+        }
+        if (rc) return rc;
+    }
     auto kern = gemm_tcgen05_kernel<BN, EPI>;
     static bool attr_set[64] = {false};   // per instantiation, per device
     int dev = 0;
@@ -354,7 +464,7 @@ static int launch_one(const void* A, const void* B, int M, int N, int K, const E
     }
     const int tiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, M, N, K, ep);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, tc, M, N, K, ep);
     return check_last("gemm");
 }
 
@@ -372,9 +482,6 @@ int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, cons
         HVLM_GEMM_CASE(EPI_GELU_BF16)
         HVLM_GEMM_CASE(EPI_RESID_F32)
         HVLM_GEMM_CASE(EPI_GELU_F32)
-        HVLM_GEMM_CASE(EPI_RESID_BF16)
-        case EPI_QKV:
-            return launch_one<256, EPI_QKV>(A, B, M, N, K, ep, s);
         case EPI_PATCH:
             return launch_one<256, EPI_PATCH>(A, B, M, N, K, ep, s);
         default:
@@ -408,10 +515,17 @@ extern "C" int hvlm_gemm_bf16(const void* A, const void* B, const float* bias, c
             break;
         case HVLM_EPI_BIAS_RESIDUAL:
             if (!resid) return HVLM_ERR_BAD_ARG;
-            epi = out_dtype == HVLM_BF16 ? EPI_RESID_BF16 : EPI_RESID_F32;
+            if (out_dtype != HVLM_F32) return HVLM_ERR_BAD_DTYPE;
+            // the kernel accumulates into the fp32 residual stream in place (TMA reduce-add)
+            if (resid != out &&
+                cudaMemcpyAsync(out, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToDevice,
+                                static_cast<cudaStream_t>(stream)) != cudaSuccess)
+                return HVLM_ERR_CUDA;
+            epi = EPI_RESID_F32;
             break;
         default:
             return HVLM_ERR_BAD_ARG;
     }
+    StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
     return launch_gemm(epi, A, B, M, N, K, ep, static_cast<cudaStream_t>(stream));
 }

@@ -93,6 +93,7 @@ extern "C" int hvlm_hand_gather_fwd(const void* hidden, int dtype, const int64_t
     if (!hidden || !labels || !out || !valid || !rows || !counts) return HVLM_ERR_BAD_ARG;
     if (B <= 0 || L <= 0 || D <= 0 || (D & 1)) return HVLM_ERR_BAD_SHAPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_GATHER, s);
     HVLM_DISPATCH_DTYPE(dtype, TT, {
         hand_gather_fwd_kernel<TT><<<B, kPlanThreads, 0, s>>>(static_cast<const TT*>(hidden), labels, hand_id, L, D,
                                                              static_cast<TT*>(out), valid, rows, counts);

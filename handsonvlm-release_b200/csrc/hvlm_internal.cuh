@@ -16,20 +16,15 @@ enum Epi : int {
     EPI_BIAS_BF16 = 0,   // out bf16 [M,N] = acc + bias
     EPI_BIAS_F32 = 1,    // out f32  [M,N] = acc + bias
     EPI_GELU_BF16 = 2,   // out bf16 [M,N] = quick_gelu(acc + bias)
-    EPI_RESID_F32 = 3,   // out f32  [M,N] = resid + acc + bias (in place allowed)
-    EPI_QKV = 4,         // ViT: scatter to q / k [F,16,257,64] and v^T [F,16,64,272]
+    EPI_RESID_F32 = 3,   // out f32  [M,N] += acc + bias  (TMA reduce-add into the residual stream, in place)
     EPI_PATCH = 5,       // ViT: x0[f*257+1+p, n] = acc + pos[1+p, n]   (f32)
-    EPI_GELU_F32 = 6,    // out f32 = quick_gelu(acc + bias)            (tests only)
-    EPI_RESID_BF16 = 7   // out bf16 = resid + acc + bias               (tests only)
+    EPI_GELU_F32 = 6     // out f32 = quick_gelu(acc + bias)            (tests only)
 };
 
 struct EpiArgs {
     const float* bias = nullptr;
     const float* resid = nullptr;
     void* out = nullptr;
-    void* q = nullptr;
-    void* k = nullptr;
-    void* vt = nullptr;
     const float* pos = nullptr;
 };
 
@@ -40,11 +35,21 @@ int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, cons
 // 2D/3D bf16 tensor map with SWIZZLE_128B and a [box_rows x 64] (x1) box.  dims/strides innermost first.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same for fp32 elements (box inner dimension 32 elements = 128 B)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
 
 int num_sms();
 int check_last(const char* what);
+void count_launch();
 
-#define HVLM_VT_STRIDE 272   // keys padded to a multiple of 8 elements (16 B) for the TMA global stride
+// RAII per-stage timing (no-op unless hvlm_profile_enable(1))
+struct StageTimer {
+    StageTimer(int stage, cudaStream_t s);
+    ~StageTimer();
+    int idx_;
+    cudaStream_t s_;
+};
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -291,6 +291,7 @@ extern "C" int hvlm_pool_slowfast_fwd(const void* tok, int in_dtype, int64_t fra
     if (!aligned16(tok) || !aligned16(out)) return HVLM_ERR_ALIGN;
     if (in_dtype == HVLM_F16 || out_dtype == HVLM_F16) return HVLM_ERR_BAD_DTYPE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_POOL, s);
     if (in_dtype == HVLM_F32 && out_dtype == HVLM_F32) return pool_fwd_typed<float, float>(tok, frame_stride, out, B, t, C, mode, s);
     if (in_dtype == HVLM_F32 && out_dtype == HVLM_BF16) return pool_fwd_typed<float, __nv_bfloat16>(tok, frame_stride, out, B, t, C, mode, s);
     if (in_dtype == HVLM_BF16 && out_dtype == HVLM_BF16) return pool_fwd_typed<__nv_bfloat16, __nv_bfloat16>(tok, frame_stride, out, B, t, C, mode, s);

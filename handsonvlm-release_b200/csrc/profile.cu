@@ -1,0 +1,79 @@
+// Launch counter and optional per-stage CUDA-event timing (used by bench.py for the roofline figures).
+// Disabled by default: the hot path records nothing and pays one relaxed atomic load per launch site.
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "hvlm_internal.cuh"
+
+namespace hvlm {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_profile_on{0};
+static std::mutex g_mu;
+struct Rec {
+    int stage;
+    cudaEvent_t a, b;
+};
+static std::vector<Rec> g_recs;
+static std::vector<cudaEvent_t> g_free;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static cudaEvent_t get_event() {
+    if (!g_free.empty()) {
+        cudaEvent_t e = g_free.back();
+        g_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+StageTimer::StageTimer(int stage, cudaStream_t s) : idx_(-1), s_(s) {
+    if (!g_profile_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Rec r{stage, get_event(), get_event()};
+    cudaEventRecord(r.a, s);
+    g_recs.push_back(r);
+    idx_ = static_cast<int>(g_recs.size()) - 1;
+}
+
+StageTimer::~StageTimer() {
+    if (idx_ < 0) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (idx_ < static_cast<int>(g_recs.size())) cudaEventRecord(g_recs[idx_].b, s_);
+}
+
+}  // namespace hvlm
+
+extern "C" uint64_t hvlm_launch_count(void) { return hvlm::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int hvlm_profile_enable(int on) {
+    hvlm::g_profile_on.store(on ? 1 : 0, std::memory_order_relaxed);
+    return HVLM_OK;
+}
+
+extern "C" int hvlm_profile_collect(float* ms_by_stage, int32_t* launches_by_stage) {
+    using namespace hvlm;
+    if (!ms_by_stage || !launches_by_stage) return HVLM_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int i = 0; i < HVLM_STAGE_COUNT; ++i) {
+        ms_by_stage[i] = 0.f;
+        launches_by_stage[i] = 0;
+    }
+    int rc = HVLM_OK;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) rc = HVLM_ERR_CUDA;
+        if (r.stage >= 0 && r.stage < HVLM_STAGE_COUNT) {
+            ms_by_stage[r.stage] += ms;
+            launches_by_stage[r.stage] += 1;
+        }
+        g_free.push_back(r.a);
+        g_free.push_back(r.b);
+    }
+    g_recs.clear();
+    return rc;
+}

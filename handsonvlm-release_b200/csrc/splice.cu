@@ -234,6 +234,7 @@ splice_bwd_kernel(const T* __restrict__ d_embeds, const int32_t* __restrict__ sr
 extern "C" int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* counts, void* stream) {
     using namespace hvlm;
     if (!ids || !counts || B <= 0 || T <= 0) return HVLM_ERR_BAD_ARG;
+    StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_count_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(ids, T, counts);
     return check_last("splice_count");
 }
@@ -246,6 +247,7 @@ extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B
     if (B <= 0 || T <= 0 || Nv <= 0 || n_img <= 0 || L <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
     if (variant != HVLM_SPLICE_LLAVA && variant != HVLM_SPLICE_HANDSONVLM) return HVLM_ERR_BAD_ARG;
     if (hand_mode < 0 || hand_mode > 2 || n_hand_points < 0 || n_hand_points > 127) return HVLM_ERR_BAD_ARG;
+    StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_plan_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, counts, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index, hand_code, lens,
         hand_scale, status);
@@ -264,6 +266,7 @@ extern "C" int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code
     if (future_hands && (!hand_code || !hand_scale || n_hand_points <= 0)) return HVLM_ERR_BAD_ARG;
     if (!aligned16(embed_table) || !aligned16(visual) || !aligned16(out_embeds)) return HVLM_ERR_ALIGN;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_SPLICE, s);
     HVLM_DISPATCH_DTYPE(dtype, TT, {
         if (D % Vec16<TT>::N != 0 || (future_hands && (D % 8) != 0)) return HVLM_ERR_BAD_SHAPE;
         splice_fwd_kernel<TT><<<dim3(L, B), 128, 0, s>>>(

@@ -5,7 +5,7 @@
 // run (23 of 24 for select_layer=-2); no hidden-state list is kept; the fp32 residual stream is the single
 // [n,257,1024] output buffer and every GEMM epilogue reads/writes it in place.
 //
-// Per layer (7 launches):  LN1 -> QKV GEMM (head-scatter epilogue) -> attention -> out_proj GEMM (+residual)
+// Per layer (7 launches):  LN1 -> QKV GEMM ([M,3072], heads read in place by TMA) -> attention -> out_proj GEMM (+residual)
 //                          -> LN2 -> fc1 GEMM (+quick-GELU) -> fc2 GEMM (+residual)
 #include "hvlm_internal.cuh"
 
@@ -14,12 +14,12 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
                      cudaStream_t s);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
-int launch_attention(const void* q, const void* k, const void* vt, void* out, int n_frames, cudaStream_t s);
+int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
 
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct VitWorkspace {
-    uint64_t a_patch, y, q, k, vt, attn, f1, total;
+    uint64_t a_patch, y, qkv, attn, f1, total;
 };
 
 static VitWorkspace vit_workspace(int n_frames) {
@@ -34,9 +34,7 @@ static VitWorkspace vit_workspace(int n_frames) {
     };
     w.a_patch = take(F * 256 * HVLM_VIT_PATCH_KPAD * 2);
     w.y = take(M * 1024 * 2);
-    w.q = take(M * 1024 * 2);
-    w.k = take(M * 1024 * 2);
-    w.vt = take(F * 16 * 64 * HVLM_VT_STRIDE * 2);
+    w.qkv = take(M * 3072 * 2);
     w.attn = take(M * 1024 * 2);
     w.f1 = take(M * 4096 * 2);
     w.total = off;
@@ -85,19 +83,6 @@ extern "C" size_t hvlm_vit_l14_workspace_bytes(int n_frames) {
     return static_cast<size_t>(hvlm::vit_workspace(n_frames).total);
 }
 
-extern "C" int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* b_qkv, void* q, void* k, void* vt,
-                                 int n_frames, void* stream) {
-    using namespace hvlm;
-    if (!A || !w_qkv || !q || !k || !vt || n_frames <= 0) return HVLM_ERR_BAD_ARG;
-    if (!aligned16(q) || !aligned16(k) || !aligned16(vt)) return HVLM_ERR_ALIGN;
-    EpiArgs ep;
-    ep.bias = b_qkv;
-    ep.q = q;
-    ep.k = k;
-    ep.vt = vt;
-    return launch_gemm(EPI_QKV, A, w_qkv, n_frames * HVLM_VIT_TOKENS, 3072, 1024, ep, static_cast<cudaStream_t>(stream));
-}
-
 extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
                                 int n_frames, float* hidden, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace hvlm;
@@ -118,47 +103,64 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
     const int M = n_frames * HVLM_VIT_TOKENS;
 
     // embeddings: im2col (+ CLS rows) -> patch GEMM (+ position embedding) -> pre_layrnorm (in place)
-    rc = launch_im2col(pixels, pix_dtype, n_frames, w8 + ws.a_patch, f32(L.cls), f32(L.pos), hidden, s);
+    {
+        StageTimer st(HVLM_STAGE_IM2COL, s);
+        rc = launch_im2col(pixels, pix_dtype, n_frames, w8 + ws.a_patch, f32(L.cls), f32(L.pos), hidden, s);
+    }
     if (rc) return rc;
     {
         EpiArgs ep;
         ep.out = hidden;
         ep.pos = f32(L.pos);
+        StageTimer st(HVLM_STAGE_PATCH_GEMM, s);
         rc = launch_gemm(EPI_PATCH, w8 + ws.a_patch, wb + L.patch_w, n_frames * 256, 1024, HVLM_VIT_PATCH_KPAD, ep, s);
         if (rc) return rc;
     }
-    rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s);
+    {
+        StageTimer st(HVLM_STAGE_LAYERNORM, s);
+        rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s);
+    }
     if (rc) return rc;
 
     for (int l = 0; l < n_layers_run; ++l) {
         const auto& y = L.layer[l];
-        rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+        {
+            StageTimer st(HVLM_STAGE_LAYERNORM, s);
+            rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+        }
         if (rc) return rc;
         {
             EpiArgs ep;
             ep.bias = f32(y.b_qkv);
-            ep.q = w8 + ws.q;
-            ep.k = w8 + ws.k;
-            ep.vt = w8 + ws.vt;
-            rc = launch_gemm(EPI_QKV, w8 + ws.y, wb + y.w_qkv, M, 3072, 1024, ep, s);
+            ep.out = w8 + ws.qkv;
+            StageTimer st(HVLM_STAGE_QKV_GEMM, s);
+            rc = launch_gemm(EPI_BIAS_BF16, w8 + ws.y, wb + y.w_qkv, M, 3072, 1024, ep, s);
             if (rc) return rc;
         }
-        rc = launch_attention(w8 + ws.q, w8 + ws.k, w8 + ws.vt, w8 + ws.attn, n_frames, s);
+        {
+            StageTimer st(HVLM_STAGE_ATTENTION, s);
+            rc = launch_attention(w8 + ws.qkv, w8 + ws.attn, n_frames, s);
+        }
         if (rc) return rc;
         {
             EpiArgs ep;
             ep.bias = f32(y.b_o);
             ep.resid = hidden;
             ep.out = hidden;
+            StageTimer st(HVLM_STAGE_OUTPROJ_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.attn, wb + y.w_o, M, 1024, 1024, ep, s);
             if (rc) return rc;
         }
-        rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+        {
+            StageTimer st(HVLM_STAGE_LAYERNORM, s);
+            rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+        }
         if (rc) return rc;
         {
             EpiArgs ep;
             ep.bias = f32(y.b_fc1);
             ep.out = w8 + ws.f1;
+            StageTimer st(HVLM_STAGE_FC1_GEMM, s);
             rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + y.w_fc1, M, 4096, 1024, ep, s);
             if (rc) return rc;
         }
@@ -167,6 +169,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
             ep.bias = f32(y.b_fc2);
             ep.resid = hidden;
             ep.out = hidden;
+            StageTimer st(HVLM_STAGE_FC2_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.f1, wb + y.w_fc2, M, 1024, 4096, ep, s);
             if (rc) return rc;
         }

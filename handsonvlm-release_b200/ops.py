@@ -197,23 +197,31 @@ def layernorm_1024(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, out_dtype=
     return out
 
 
-def vit_qkv(y: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, n_frames: int):
-    _need_cuda(y, w_qkv, b_qkv)
-    dev = y.device
-    q = torch.empty(n_frames, 16, 257, 64, dtype=torch.bfloat16, device=dev)
-    k = torch.empty_like(q)
-    vt = torch.zeros(n_frames, 16, 64, 272, dtype=torch.bfloat16, device=dev)
-    L.check(L.lib().hvlm_vit_qkv_gemm(_p(y), _p(w_qkv), _p(b_qkv), _p(q), _p(k), _p(vt), n_frames, _stream()),
-            "hvlm_vit_qkv_gemm")
-    return q, k, vt
-
-
-def vit_attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor) -> torch.Tensor:
-    _need_cuda(q, k, vt)
-    n_frames = q.shape[0]
-    out = torch.empty(n_frames * 257, 1024, dtype=torch.bfloat16, device=q.device)
-    L.check(L.lib().hvlm_vit_attention(_p(q), _p(k), _p(vt), _p(out), n_frames, _stream()), "hvlm_vit_attention")
+def vit_attention(qkv: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """qkv bf16 [n_frames*257, 3072] (q|k|v, q pre-scaled) -> bf16 [n_frames*257, 1024]."""
+    _need_cuda(qkv)
+    ensure_device()
+    assert qkv.dtype == torch.bfloat16 and tuple(qkv.shape) == (n_frames * 257, 3072) and qkv.is_contiguous()
+    out = torch.empty(n_frames * 257, 1024, dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.lib().hvlm_vit_attention(_p(qkv), _p(out), n_frames, _stream()), "hvlm_vit_attention")
     return out
+
+
+def launch_count() -> int:
+    return int(L.lib().hvlm_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    L.lib().hvlm_profile_enable(int(on))
+
+
+def profile_collect() -> dict:
+    """-> {stage: (device_ms, launches)} summed over everything recorded since profile_enable(True)."""
+    n = len(L.STAGES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int32 * n)()
+    L.check(L.lib().hvlm_profile_collect(ms, cnt), "hvlm_profile_collect")
+    return {L.STAGES[i]: (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -145,11 +145,9 @@ HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames,
 /* building blocks of the tower, exported for per-stage parity tests */
 HVLM_API int hvlm_layernorm_1024(const float* x, const float* gamma, const float* beta, void* out, int rows, int out_dtype,
                         float eps, void* stream);
-/* A [M=n_frames*257,1024] bf16 -> q,k [n_frames,16,257,64] bf16 ; vt [n_frames,16,64,272] bf16 (keys padded) */
-HVLM_API int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* b_qkv, void* q, void* k, void* vt,
-                      int n_frames, void* stream);
-/* softmax(q k^T) v per (frame, head); q already carries the 64^-1/2 scale. out bf16 [n_frames*257, 1024] */
-HVLM_API int hvlm_vit_attention(const void* q, const void* k, const void* vt, void* out, int n_frames, void* stream);
+/* qkv bf16 [n_frames*257, 3072] = LN1(x) W_qkv^T + b (columns q | k | v, 16 heads x 64 each; q carries the
+ * 64^-1/2 scale) -> out bf16 [n_frames*257, 1024] = concat_heads(softmax(q k^T) v).  Heads are read in place by TMA. */
+HVLM_API int hvlm_vit_attention(const void* qkv, void* out, int n_frames, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LITA slow-fast token pooling -- replaces
@@ -233,6 +231,32 @@ HVLM_API int hvlm_hand_gather_step(const void* hidden_last, int dtype, int B, in
 HVLM_API int hvlm_transpose_to_bf16(const void* in, int in_dtype, void* out, int R, int C, int R_pad, void* stream);
 /* db[n] = sum_m dY[m,n]  (fp32) */
 HVLM_API int hvlm_colsum(const void* dy, int dtype, float* db, int M, int N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * measurement hooks (bench.py): number of kernels this library has launched in the process, and optional
+ * per-stage device timing with CUDA events recorded on the launching stream around every launch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+    HVLM_STAGE_IM2COL = 0,
+    HVLM_STAGE_PATCH_GEMM = 1,
+    HVLM_STAGE_LAYERNORM = 2,
+    HVLM_STAGE_QKV_GEMM = 3,
+    HVLM_STAGE_ATTENTION = 4,
+    HVLM_STAGE_OUTPROJ_GEMM = 5,
+    HVLM_STAGE_FC1_GEMM = 6,
+    HVLM_STAGE_FC2_GEMM = 7,
+    HVLM_STAGE_POOL = 8,
+    HVLM_STAGE_GEMM = 9,        /* hvlm_gemm_bf16: projector fwd / wgrad */
+    HVLM_STAGE_SPLICE = 10,
+    HVLM_STAGE_GATHER = 11,
+    HVLM_STAGE_OTHER = 12,
+    HVLM_STAGE_COUNT = 13
+} hvlm_stage;
+
+HVLM_API uint64_t hvlm_launch_count(void);
+HVLM_API int hvlm_profile_enable(int on);
+/* synchronises the recorded events, sums device ms and launches per stage, clears the record list */
+HVLM_API int hvlm_profile_collect(float* ms_by_stage_host /*[HVLM_STAGE_COUNT]*/, int32_t* launches_by_stage_host);
 
 #ifdef __cplusplus
 }

@@ -259,7 +259,11 @@ def test_splice_llava_vs_reference_fixture(golden, small, name, pxshape, pxseed,
     else:
         vis = _small_visual(small, px)
     m2, e2, l2 = _splice_cuda(L.SPLICE_LLAVA, T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, emb.weight.data)
-    assert torch.equal(e2.cpu(), T(g["embeds"]))         # pure copies: bit-exact
+    # visual rows come from the CPU oracle run on THIS host (thread-count dependent rounding vs the fixture);
+    # every row is a pure copy of its source, which is checked bit-exactly against the oracle's own splice
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    rm, re_, rl = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, emb.weight.data, "llava")
+    assert torch.equal(e2.cpu(), re_)
     assert torch.equal(l2.cpu(), T(g["labels"]))
     assert m2.dtype == torch.bool and torch.equal(m2.cpu(), T(g["mask"]))
 
@@ -306,15 +310,14 @@ def test_qkv_and_attention_stage():
     y = synth.gen("attn.y", (F * 257, 1024), 1.0, 1).to(torch.bfloat16)
     w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
     b = synth.gen("attn.b", (3072,), 0.1, 1)
-    q, k, vt = ops.vit_qkv(y.to(DEV), w.to(DEV), b.to(DEV), F)
-    ref = (y.float() @ w.float().t() + b).reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)
-    assert relmax(q, ref[0]) <= 5e-3 and relmax(k, ref[1]) <= 5e-3
-    assert relmax(vt[..., :257], ref[2].transpose(-1, -2)) <= 5e-3
+    qkv = ops.gemm(y.to(DEV), w.to(DEV), b.to(DEV))
+    assert relmax(qkv, y.float() @ w.float().t() + b) <= 5e-3
     for scale in (0.125, 1.0):
-        qs = (q.float() * scale).to(torch.bfloat16)
-        o = ops.vit_attention(qs, k, vt)
-        s = qs.float().cpu() @ k.float().cpu().transpose(-1, -2)
-        oref = (torch.softmax(s, -1) @ vt[..., :257].float().cpu().transpose(-1, -2)).permute(0, 2, 1, 3).reshape(F * 257, 1024)
+        q2 = qkv.clone()
+        q2[:, :1024] = (q2[:, :1024].float() * scale).to(torch.bfloat16)
+        o = ops.vit_attention(q2, F)
+        t = q2.float().cpu().reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)
+        oref = (torch.softmax(t[0] @ t[1].transpose(-1, -2), -1) @ t[2]).permute(0, 2, 1, 3).reshape(F * 257, 1024)
         assert relmax(o, oref) <= 8e-3
 
 

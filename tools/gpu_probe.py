@@ -133,45 +133,42 @@ def _attn_ref(q, k, v):
     return torch.softmax(s, -1) @ v
 
 
+def _attn_ref_from_qkv(qkv, F):
+    t = qkv.float().cpu().reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)   # [3,F,16,257,64]
+    s = t[0] @ t[1].transpose(-1, -2)
+    return (torch.softmax(s, -1) @ t[2]).permute(0, 2, 1, 3).reshape(F * 257, 1024)
+
+
 def stage_attn():
     F = 3
     y = synth.gen("attn.y", (F * 257, 1024), 1.0, 1).to(torch.bfloat16)
     w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
     w[:1024] *= 0.125
     b = synth.gen("attn.b", (3072,), 0.1, 1)
-    q, k, vt = ops.vit_qkv(y.to(dev), w.to(dev), b.to(dev), F)
-    ref = (y.float() @ w.float().t() + b).reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)   # [3,F,16,257,64]
-    stats("qkv_q", q, ref[0])
-    stats("qkv_k", k, ref[1])
-    stats("qkv_vt", vt[..., :257], ref[2].transpose(-1, -2))
-    print("vt pad zero:", float(vt[..., 257:].abs().max()))
-    qf, kf, vf = q.float().cpu(), k.float().cpu(), vt[..., :257].float().cpu().transpose(-1, -2)
-    o = ops.vit_attention(q, k, vt)
-    oref = _attn_ref(qf, kf, vf).permute(0, 2, 1, 3).reshape(F * 257, 1024)
-    stats("attention", o, oref)
-    # sharper distribution
-    q2 = (q.float() * 6).to(torch.bfloat16)
-    o2 = ops.vit_attention(q2, k, vt)
-    stats("attention_sharp", o2, _attn_ref(q2.float().cpu(), kf, vf).permute(0, 2, 1, 3).reshape(F * 257, 1024))
+    qkv = ops.gemm(y.to(dev), w.to(dev), b.to(dev))
+    stats("qkv_gemm", qkv, y.float() @ w.float().t() + b)
+    stats("attention", ops.vit_attention(qkv, F), _attn_ref_from_qkv(qkv, F))
+    qkv2 = qkv.clone()
+    qkv2[:, :1024] *= 6
+    stats("attention_sharp", ops.vit_attention(qkv2, F), _attn_ref_from_qkv(qkv2, F))
     Fb = 100
-    qb = torch.randn(Fb, 16, 257, 64, device=dev).to(torch.bfloat16) * 0.3
-    kb = torch.randn(Fb, 16, 257, 64, device=dev).to(torch.bfloat16)
-    vb = torch.zeros(Fb, 16, 64, 272, device=dev, dtype=torch.bfloat16)
-    vb[..., :257] = torch.randn(Fb, 16, 64, 257, device=dev).to(torch.bfloat16)
+    qb = torch.randn(Fb * 257, 3072, device=dev).to(torch.bfloat16)
+    qb[:, :1024] *= 0.3
     for _ in range(3):
-        ob = ops.vit_attention(qb, kb, vb)
+        ob = ops.vit_attention(qb, Fb)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        ops.vit_attention(qb, kb, vb)
+        ops.vit_attention(qb, Fb)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     RES["time_attn_100f"] = dict(ms=ms, tflops=Fb * 16 * 4 * 257 * 257 * 64 / ms / 1e9)
     print(f"attention 100 frames: {ms:.3f} ms", flush=True)
+    t = qb.reshape(Fb, 257, 3, 16, 64).permute(2, 0, 3, 1, 4).float()
     stats("attention_big_vs_sdpa", ob.reshape(Fb, 257, 16, 64).permute(0, 2, 1, 3),
-          torch.nn.functional.scaled_dot_product_attention(qb.float(), kb.float(), vb[..., :257].float().transpose(-1, -2), scale=1.0))
+          torch.nn.functional.scaled_dot_product_attention(t[0], t[1], t[2], scale=1.0))
 
 
 def stage_vit():
@@ -214,6 +211,17 @@ def stage_bench():
     ms = e0.elapsed_time(e1) / 5
     RES["time_vit_100f"] = dict(ms=ms, frames_per_s=100 / ms * 1e3, tflops=100 * 155.29 / ms)
     print(f"ViT 100 frames: {ms:.2f} ms  {100/ms*1e3:.0f} frames/s  {100*155.29/ms:.0f} TF/s", flush=True)
+    ops.profile_enable(True)
+    for _ in range(3):
+        tower.forward_hidden(px)
+    prof = ops.profile_collect()
+    ops.profile_enable(False)
+    flops = dict(qkv_gemm=2 * 25700 * 3072 * 1024, outproj_gemm=2 * 25700 * 1024 * 1024, fc1_gemm=2 * 25700 * 4096 * 1024,
+                 fc2_gemm=2 * 25700 * 4096 * 1024, attention=1600 * 4 * 257 * 257 * 64)
+    for k, (t, n) in prof.items():
+        extra = f"  {flops[k] / (t / n) / 1e9:7.0f} TF/s" if k in flops else ""
+        print(f"  {k:14s} {t / 3:8.3f} ms/fwd  n={n // 3:3d}  avg {t / n * 1e3:7.1f} us{extra}", flush=True)
+    RES["profile"] = {k: dict(ms_per_fwd=t / 3, launches=n // 3) for k, (t, n) in prof.items()}
 
 
 if __name__ == "__main__":
