@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- video frames/s of the HandsOnVLM visual-token prep path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the drop-in API)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU restatement of the reference
+                                                           path (oracle port) on the box's host cores
+
+A "step" = one pass of the hot path over one batch of synthetic input on every rank:
+    [B clips x 100 frames x 3 x 224 x 224] -> CLIP ViT-L/14 (23 layers) -> LITA slow-fast pooling (356 tokens)
+    -> mm_projector 1024->4096 -> splice into the Vicuna embedding sequence (+labels/mask, hand embeddings)
+    -> <hand_traj> hidden-state gather.
+Workload at N=1: BASELINE.json configs[1] ("HandsOnVLM-7B video clip: 100 frames ... bf16, batch 1, 1x B200").
+For N>1 every rank processes its own clip(s) (clips shard by index, no collective in the forward path): weak scaling.
+
+value : frames/s, inputs resident in HBM, timed on the device with CUDA events over exactly K steps, max over ranks
+e2e   : same metric through the same public API with HOST (pinned) inputs: H2D of the clip + prompt and D2H of the
+        gathered hand states inside the timed region, wall clock between device synchronisations, max over ranks
+Timing hygiene: W >= 3 warm-up steps; the per-step working set (582 MB of weights + ~0.5 GB of activations per
+clip) is several times the 126 MB L2, so no explicit L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+import types
+import zlib
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FRAMES = 100
+VIT_GFLOP_PER_FRAME = 155.29           # 23 layers + patch embed
+T_PROMPT = 62                          # 35 ++ [-200] ++ 20 ++ [32100]x4 ++ [869, 2]   
+VOCAB = 32101
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic weights / inputs (no network: random init of the named architecture)
+# ------------------------------------------------------------------------------------------------
+def _gen(name, shape, std, seed=0, mean=0.0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(name.encode()) ^ ((seed + 1) * 0x9E3779B1)) & 0x7FFFFFFF)
+    return torch.randn(tuple(shape), generator=g, dtype=torch.float32).mul_(std).add_(mean)
+
+
+def clip_state_dict(n_layers=24, seed=0):
+    """HF-named CLIPVisionModel ViT-L/14 state dict, HF-init-like stds (biases / LN affine perturbed)."""
+    E, FF, L = 1024, 4096, 24
+    s_in = (E ** -0.5) * ((2 * L) ** -0.5)
+    p = "vision_model."
+    sd = {p + "embeddings.class_embedding": _gen("cls", (E,), E ** -0.5, seed),
+          p + "embeddings.patch_embedding.weight": _gen("patch", (E, 3, 14, 14), 0.02, seed),
+          p + "embeddings.position_embedding.weight": _gen("pos", (257, E), 0.02, seed),
+          p + "pre_layrnorm.weight": _gen("preln.w", (E,), 0.1, seed, 1.0),
+          p + "pre_layrnorm.bias": _gen("preln.b", (E,), 0.05, seed)}
+    for l in range(n_layers):
+        q = f"{p}encoder.layers.{l}."
+        for nm, std in (("q_proj", s_in), ("k_proj", s_in), ("v_proj", s_in), ("out_proj", E ** -0.5)):
+            sd[f"{q}self_attn.{nm}.weight"] = _gen(f"l{l}.{nm}.w", (E, E), std, seed)
+            sd[f"{q}self_attn.{nm}.bias"] = _gen(f"l{l}.{nm}.b", (E,), 0.02, seed)
+        for nm in ("layer_norm1", "layer_norm2"):
+            sd[f"{q}{nm}.weight"] = _gen(f"l{l}.{nm}.w", (E,), 0.1, seed, 1.0)
+            sd[f"{q}{nm}.bias"] = _gen(f"l{l}.{nm}.b", (E,), 0.05, seed)
+        sd[q + "mlp.fc1.weight"] = _gen(f"l{l}.fc1.w", (FF, E), s_in, seed)
+        sd[q + "mlp.fc1.bias"] = _gen(f"l{l}.fc1.b", (FF,), 0.02, seed)
+        sd[q + "mlp.fc2.weight"] = _gen(f"l{l}.fc2.w", (E, FF), (2 * E) ** -0.5, seed)
+        sd[q + "mlp.fc2.bias"] = _gen(f"l{l}.fc2.b", (E,), 0.02, seed)
+    return sd
+
+
+def make_prompt(B, seed=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1234 + seed)
+    ids = torch.randint(1, 32000, (B, T_PROMPT), generator=g, dtype=torch.int64)
+    ids[:, 35] = -200
+    ids[:, 56:60] = 32100
+    ids[:, 60] = 869
+    ids[:, 61] = 2
+    labels = ids.clone()
+    labels[:, :56] = -100
+    mask = torch.ones(B, T_PROMPT, dtype=torch.bool)
+    future_hands = torch.rand(B, 2, 4, 2, generator=g)
+    future_valid = torch.ones(B, 2, dtype=torch.bool)
+    return ids, mask, labels, future_hands, future_valid
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+                pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(pw)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_host(D, dev, sd):
+    import hvlm_b200
+    from hvlm_b200 import arch
+    from hvlm_b200.tower import CLIPVisionTower
+
+    tower = CLIPVisionTower("synthetic-vit-l14", types.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    tower.load_model(sd)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(_gen("proj.w", (D, 1024), 0.018, 1))
+    proj.bias.data.copy_(_gen("proj.b", (D,), 0.018, 1))
+    emb = torch.nn.Embedding(VOCAB, D)
+    emb.weight.data.copy_(_gen("embed_tokens", (VOCAB, D), 1.0, 1))
+
+    class Inner(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.vision_tower, self.mm_projector, self.embed_tokens = tower, proj.to(torch.bfloat16), emb.to(torch.bfloat16)
+
+        def get_vision_tower(self):
+            return self.vision_tower
+
+    class Host(torch.nn.Module, arch.HandsOnVLMMetaForCausalLM):
+        def __init__(self):
+            super().__init__()
+            self.model = Inner()
+            self.config = types.SimpleNamespace(fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool",
+                                                mm_hidden_size=1024, input_type="video", hvlm_static_splice=True)
+            self.token_dim, self.B = D, None
+
+        def get_model(self):
+            return self.model
+
+    return Host().to(dev)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                        src="measured (MEASURED_PEAKS.json)")
+        except Exception:
+            pass
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def traffic_for(kernel):
+    """dram bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    from hvlm_b200 import dist as hd
+    from hvlm_b200 import ops
+    import torch.distributed as dist
+
+    rank, world, local = hd.env_rank_world()
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    hd.init_process_group("nccl" if world > 1 else None)
+    ops.ensure_device()
+    D, B = args.hidden, args.clips
+    sd = clip_state_dict(23)
+    host = build_host(D, dev, sd)
+    host.B = B
+
+    ids, mask, labels, fh, fv = make_prompt(B, seed=rank)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(100 + rank)
+    px_host = torch.randn(B, FRAMES, 3, 224, 224, generator=g).to(torch.bfloat16).pin_memory()
+    host_in = [t.pin_memory() for t in (ids, mask, labels, fh, fv)]
+    px = px_host.to(dev)
+    dev_in = [t.to(dev) for t in host_in]
+    hidden_dev = torch.randn(B, T_PROMPT + 355, D, device=dev, dtype=torch.bfloat16)   # stands in for the LLM output
+    out_host = torch.empty(B, 2, 4, D // 2, dtype=torch.bfloat16).pin_memory()
+
+    def step(pixels, ins):
+        i, m, l, f, v = ins
+        with torch.no_grad():
+            r = host.prepare_inputs_labels_for_multimodal(i, m, None, l, pixels, future_hands=f, future_valid=v,
+                                                          is_evaluate=False)
+            gout, valid = host.gather_hand_traj_states(hidden_dev, r[4], future_valid=v, strict=False)
+        return r, gout
+
+    for _ in range(max(args.warmup, 3)):
+        step(px, dev_in)
+    torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, CUDA events, max over ranks
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    hd.barrier()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(px, dev_in)
+    e1.record()
+    torch.cuda.synchronize()
+    hd.barrier()
+    launches = ops.launch_count() - l0
+    ms_total = hd.max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    frames_per_step = B * FRAMES * world
+    value = frames_per_step / (ms_step / 1e3)
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region, wall clock
+    def e2e_step():
+        pixels = px_host.to(dev, non_blocking=True)
+        ins = [t.to(dev, non_blocking=True) for t in host_in]
+        r, gout = step(pixels, ins)
+        out_host.copy_(gout, non_blocking=True)
+        return r
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    hd.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = hd.max_over_ranks(time.perf_counter() - t0, dev)
+    hd.barrier()
+    h2d = px_host.numel() * px_host.element_size() + sum(t.numel() * t.element_size() for t in host_in)
+    d2h = out_host.numel() * out_host.element_size()
+    e2e_value = frames_per_step * args.steps / e2e_s
+
+    # ---- per-stage device times (CUDA events on the launching stream around every launch), rank 0
+    res = None
+    if rank == 0:
+        ops.profile_enable(True)
+        for _ in range(2):
+            step(px, dev_in)
+        prof = ops.profile_collect()
+        ops.profile_enable(False)
+        pk = peaks()
+        M = B * FRAMES * 257
+        flops = {"qkv_gemm": 2 * M * 3072 * 1024, "outproj_gemm": 2 * M * 1024 * 1024, "fc1_gemm": 2 * M * 4096 * 1024,
+                 "fc2_gemm": 2 * M * 1024 * 4096, "patch_gemm": 2 * B * FRAMES * 256 * 1024 * 588,
+                 "attention": B * FRAMES * 16 * 4 * 257 * 257 * 64}
+        bytes_ = {"layernorm": M * 1024 * (4 + 2), "pool": B * (FRAMES * 256 * 1024 * 4 + 356 * 1024 * 2),
+                  "splice": B * ((T_PROMPT - 1 + 356) * D * 2 + (T_PROMPT + 355) * (D * 2 + 9))}
+        stages = {}
+        for k, (t, n) in prof.items():
+            avg_ms = t / n
+            st = {"ms_per_step": round(t / 2, 4), "launches_per_step": n // 2, "avg_us": round(avg_ms * 1e3, 2)}
+            if k in flops:
+                st["tflops"] = round(flops[k] / avg_ms / 1e9, 1)
+                st["frac_of_sustained_peak"] = round(st["tflops"] / pk["tf_sustained"], 3)
+            if k in bytes_:
+                per_launch = bytes_[k] / (1 if k != "splice" else 3)
+                st["gbs"] = round(per_launch / avg_ms / 1e6, 1)
+                st["frac_of_hbm_peak"] = round(st["gbs"] / pk["hbm"], 3)
+            stages[k] = st
+        dom = "fc1_gemm"
+        achieved = stages[dom]["tflops"]
+        roofline = {"kernel": "gemm_tcgen05_kernel<256, EPI_GELU_BF16> (ViT fc1: M=%d N=4096 K=1024)" % M,
+                    "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": round(achieved / pk["tf_sustained"], 4),
+                    "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
+                    "traffic": traffic_for("fc1_gemm")}
+        # whole-GEMM aggregate, for context
+        gemm_ms = sum(stages[k]["ms_per_step"] for k in ("qkv_gemm", "outproj_gemm", "fc1_gemm", "fc2_gemm") if k in stages)
+        gemm_fl = sum(flops[k] for k in ("qkv_gemm", "outproj_gemm", "fc1_gemm", "fc2_gemm")) * 23
+        res = {
+            "metric": "video frames/sec visual-token prep (ViT+pool+proj+splice)", "value": round(value, 1),
+            "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (random-init ViT-L/14 + projector + embedding table, randn pixels)",
+            "config": {"workload": "configs[1]: HandsOnVLM-7B clip, %d clip(s)/GPU x 100 frames 224x224 -> CLIP ViT-L/14 "
+                                   "(23 layers) -> LITA slow-fast pool (356 tokens) -> projector 1024->%d -> splice "
+                                   "(T=62 -> 417) + <hand_traj> gather" % (B, D),
+                       "clips_per_gpu": B, "frames_per_clip": FRAMES, "hidden": D, "parallelism": f"clip-sharded dp{world}",
+                       "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_s / args.steps * 1e3, 3)},
+            "gpu_launches": int(launches),
+            "model_tflops": round(value * VIT_GFLOP_PER_FRAME / 1e3 / world, 1),
+            "roofline": roofline,
+            "gemm_aggregate": {"tflops": round(gemm_fl / gemm_ms / 1e9, 1), "ms_per_step": round(gemm_ms, 3)},
+            "stages": stages, "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_baseline(sd, D, sample_frames=args.cpu_sample_frames)
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_path_once(px, sd, pw, pb, table, ids, mask, labels, fh):
+    """The reference path restated on CPU (fp32).  The reference executes all 24 encoder layers and keeps every
+    hidden state (clip_encoder.py:48); the port does the same and then selects hidden_states[-2]."""
+    from oracle import restate
+    b, t = px.shape[:2]
+    hs = restate.vit_hidden(px.reshape(b * t, 3, 224, 224), sd, 24, return_all=True)
+    feats = hs[-2][:, 1:]
+    tok = restate.project(feats, pw, pb).reshape(b, t, 256, -1)
+    vis = restate.pool_tokens(tok, "temporal_spatial_pool")
+    m2, e2, l2 = restate.splice(ids, mask, labels, vis, table, "handsonvlm", future_hands=fh)
+    hidden = torch.zeros_like(e2)
+    return restate.gather_hand_traj(hidden, l2)[0]
+
+
+def _cpu_setup(D, sd=None):
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = clip_state_dict(24) if sd is None or "vision_model.encoder.layers.23.mlp.fc1.weight" not in sd else sd
+    if "vision_model.encoder.layers.23.mlp.fc1.weight" not in sd:
+        sd = clip_state_dict(24)
+    pw, pb = _gen("proj.w", (D, 1024), 0.018, 1), _gen("proj.b", (D,), 0.018, 1)
+    table = _gen("embed_tokens", (VOCAB, D), 1.0, 1)
+    return sd, pw, pb, table
+
+
+def cpu_baseline(sd, D, sample_frames=8):
+    sd24 = dict(sd)
+    sd24.update({k: v for k, v in clip_state_dict(24).items() if ".layers.23." in k})
+    _, pw, pb, table = _cpu_setup(D, sd24)
+    ids, mask, labels, fh, fv = make_prompt(1)
+    px = torch.randn(1, sample_frames, 3, 224, 224)
+    with torch.no_grad():
+        _cpu_path_once(px[:, :2], sd24, pw, pb, table, ids, mask, labels, fh)      # warm-up (thread pool, MKL)
+        t0 = time.perf_counter()
+        _cpu_path_once(px, sd24, pw, pb, table, ids, mask, labels, fh)
+        dt = time.perf_counter() - t0
+    return {"value": round(sample_frames / dt, 3), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_frames}-frame clip (of the 100-frame workload) through the fp32 torch-CPU restatement of the "
+                      f"reference path (24-layer ViT as executed by the reference, projector on all tokens, pool, splice, "
+                      f"gather); {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D = args.hidden
+    sd, pw, pb, table = _cpu_setup(D)
+    ids, mask, labels, fh, fv = make_prompt(1)
+    n = args.cpu_sample_frames_ref
+    px = torch.randn(1, n, 3, 224, 224)
+    with torch.no_grad():
+        for _ in range(min(args.warmup, 2)):
+            _cpu_path_once(px, sd, pw, pb, table, ids, mask, labels, fh)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _cpu_path_once(px, sd, pw, pb, table, ids, mask, labels, fh)
+        dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"each step = a {n}-frame clip (bounded sample of the 100-frame workload) through the fp32 torch-CPU "
+              f"restatement of the reference path, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "video frames/sec visual-token prep (ViT+pool+proj+splice)", "value": round(value, 3),
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
+        "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] (bounded sample): HandsOnVLM-7B clip path on host cores", "hidden": D,
+                   "frames_per_step": n},
+        "cpu_baseline": {"value": round(value, 3), "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hidden", type=int, default=4096, help="LLM hidden size D (4096 = 7B, 5120 = 13B)")
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
+    ap.add_argument("--cpu-sample-frames", type=int, default=8)
+    ap.add_argument("--cpu-sample-frames-ref", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
