@@ -50,6 +50,7 @@ SIGNATURES = {
     "hvlm_vit_l14_fwd": (i32, [p, i32, p, i32, i32, p, p, sz, p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
+    "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, i32, p]),
     "hvlm_vit_attention": (i32, [p, p, i32, p]),
     "hvlm_pool_out_tokens": (i32, [i32, i32]),
     "hvlm_pool_slowfast_fwd": (i32, [p, i32, i64, p, i32, i32, i32, i32, i32, p]),

@@ -14,6 +14,8 @@
 // Replaces every nn.Linear on the path (see include/hvlm_b200.h).
 #include <cudaTypedefs.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "hvlm_internal.cuh"
@@ -54,6 +56,8 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base,
                           const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("HVLM_DEBUG"))
+        fprintf(stderr, "[hvlm] cuTensorMapEncodeTiled failed: CUresult %d (rank %d)\n", static_cast<int>(r), rank);
     return r == CUDA_SUCCESS ? HVLM_OK : HVLM_ERR_CUDA;
 }
 
@@ -78,9 +82,11 @@ int num_sms() {
     return cached[dev];
 }
 
-int check_last(const char*) {
+int check_last(const char* what) {
     count_launch();
-    return cudaGetLastError() == cudaSuccess ? HVLM_OK : HVLM_ERR_CUDA;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && getenv("HVLM_DEBUG")) fprintf(stderr, "[hvlm] %s: %s\n", what, cudaGetErrorString(e));
+    return e == cudaSuccess ? HVLM_OK : HVLM_ERR_CUDA;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -110,7 +116,7 @@ __device__ __forceinline__ float quick_gelu(float x) {
 template <int EPI>
 __host__ __device__ constexpr bool epi_is_staged() {
     return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_F32 || EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32 ||
-           EPI == EPI_RESID_F32;
+           EPI == EPI_RESID_F32 || EPI == EPI_QKV_HM;
 }
 template <int EPI>
 __host__ __device__ constexpr bool epi_out_f32() {
@@ -258,41 +264,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / num_n;
-                const int n_blk = tile - m_blk * num_n;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+        // The whole warp walks the loop (warp-uniform control flow and operands); one elected lane issues.
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x) {
+            const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
+            const int m_blk = tile / num_n;
+            const int n_blk = tile - m_blk * num_n;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     tma_load_2d(smem_a + stage * Cfg::kABytes, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
                     tma_load_2d(smem_b + stage * Cfg::kBBytes, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        // Whole warp in the loop, tcgen05.mma / tcgen05.commit issued by one elected lane (keeps the descriptors
+        // in uniform registers and avoids a per-instruction divergence loop).
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-                    const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+                const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+                const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // +32 bytes (encoded >>4 => +2) per 16-element K step inside the 128-byte swizzle row
@@ -300,16 +311,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
-                if (++acc == 2) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
             }
         }
     } else {
@@ -326,9 +338,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             constexpr int kUnits = BN / kUnitCols;
             const int row = q * 32 + lane;
             const int sw = row & 7;
-            const bool issuer = (warp == 2 && lane == 0);
+            const bool store_warp = (warp == 2);   // one elected lane of this warp issues the TMA stores
             uint32_t ucount = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x) {
+                const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
                 const int m_blk = tile / num_n;
                 const int n_blk = tile - m_blk * num_n;
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -338,7 +351,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 for (int u = 0; u < kUnits; ++u, ++ucount) {
                     uint8_t* buf = smem_c + (ucount & 1u) * Cfg::kStoreBuf;
                     uint8_t* brow = buf + row * 128;
-                    if (issuer) bulk_wait_read<1>();              // the store that last used this buffer is done
+                    if (store_warp) {
+                        if (elect_one()) bulk_wait_read<1>();     // the store that last used this buffer is done
+                        __syncwarp();
+                    }
                     named_bar_sync(1, 128);
                     const int n0 = n_blk * BN + u * kUnitCols;
 #pragma unroll
@@ -372,12 +388,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);
-                    if (issuer) {
-                        if constexpr (EPI == EPI_RESID_F32)
+                    if (store_warp) {
+                      if (elect_one()) {
+                        if constexpr (EPI == EPI_RESID_F32) {
                             tma_reduce_add_2d(&tma_c, buf, n0, m_blk * BM);
-                        else
+                        } else if constexpr (EPI == EPI_QKV_HM) {
+                            // column-block-major [48][M][64]: the 64-column unit is one column block
+                            tma_store_3d(&tma_c, buf, 0, m_blk * BM, n0 >> 6);
+                        } else {
                             tma_store_2d(&tma_c, buf, n0, m_blk * BM);
+                        }
                         bulk_commit();
+                      }
+                      __syncwarp();
                     }
                 }
                 if (++acc == 2) {
@@ -385,9 +408,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                     acc_phase ^= 1u;
                 }
             }
-            if (issuer) bulk_wait<0>();
+            if (store_warp) {
+                if (elect_one()) bulk_wait<0>();
+                __syncwarp();
+            }
         } else {
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int t_ = blockIdx.x; t_ < num_tiles; t_ += gridDim.x) {
+                const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
                 const int m_blk = tile / num_n;
                 const int n_blk = tile - m_blk * num_n;
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -442,7 +469,10 @@ static int launch_one(const void* A, const void* B, int M, int N, int K, const E
         if (!ep.out || !aligned16(ep.out)) return HVLM_ERR_ALIGN;
         uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
         int rc;
-        if constexpr (epi_out_f32<EPI>()) {
+        if constexpr (EPI == EPI_QKV_HM) {
+            if (N != 3072) return HVLM_ERR_BAD_SHAPE;
+            rc = make_qkv_hm_tmap(&tc, ep.out, M, BM);
+        } else if constexpr (epi_out_f32<EPI>()) {
             uint64_t str[1] = {static_cast<uint64_t>(N) * 4};
             uint32_t box[2] = {32, BM};
             rc = make_tmap_f32(&tc, ep.out, 2, dims, str, box);
@@ -484,6 +514,8 @@ int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, cons
         HVLM_GEMM_CASE(EPI_GELU_F32)
         case EPI_PATCH:
             return launch_one<256, EPI_PATCH>(A, B, M, N, K, ep, s);
+        case EPI_QKV_HM:
+            return launch_one<256, EPI_QKV_HM>(A, B, M, N, K, ep, s);
         default:
             return HVLM_ERR_BAD_ARG;
     }

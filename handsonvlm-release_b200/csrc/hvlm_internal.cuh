@@ -17,6 +17,7 @@ enum Epi : int {
     EPI_BIAS_F32 = 1,    // out f32  [M,N] = acc + bias
     EPI_GELU_BF16 = 2,   // out bf16 [M,N] = quick_gelu(acc + bias)
     EPI_RESID_F32 = 3,   // out f32  [M,N] += acc + bias  (TMA reduce-add into the residual stream, in place)
+    EPI_QKV_HM = 4,      // ViT: bf16 q|k|v written column-block-major [48][M][64] (3-D TMA stores)
     EPI_PATCH = 5,       // ViT: x0[f*257+1+p, n] = acc + pos[1+p, n]   (f32)
     EPI_GELU_F32 = 6     // out f32 = quick_gelu(acc + bias)            (tests only)
 };
@@ -26,6 +27,7 @@ struct EpiArgs {
     const float* resid = nullptr;
     void* out = nullptr;
     const float* pos = nullptr;
+    int reverse = 0;   // walk the tiles last-to-first (start with what the producer kernel left in L2)
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue.  Returns an hvlm_status.
@@ -39,6 +41,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
+int make_qkv_hm_tmap(CUtensorMap* out, const void* qkv_hm, int n_rows, int box_rows);
 int num_sms();
 int check_last(const char* what);
 void count_launch();

@@ -5,13 +5,15 @@
 // run (23 of 24 for select_layer=-2); no hidden-state list is kept; the fp32 residual stream is the single
 // [n,257,1024] output buffer and every GEMM epilogue reads/writes it in place.
 //
-// Per layer (7 launches):  LN1 -> QKV GEMM ([M,3072], heads read in place by TMA) -> attention -> out_proj GEMM (+residual)
+// Per layer (7 launches):  LN1 -> QKV GEMM (column-block-major q|k|v [48][M][64] via 3-D TMA stores) -> attention -> out_proj GEMM (+residual)
 //                          -> LN2 -> fc1 GEMM (+quick-GELU) -> fc2 GEMM (+residual)
+#include <cstdlib>
+
 #include "hvlm_internal.cuh"
 
 namespace hvlm {
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s);
+                     cudaStream_t s, int reverse);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
 int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
@@ -83,6 +85,18 @@ extern "C" size_t hvlm_vit_l14_workspace_bytes(int n_frames) {
     return static_cast<size_t>(hvlm::vit_workspace(n_frames).total);
 }
 
+extern "C" int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* b_qkv, void* qkv_hm, int n_frames,
+                                 void* stream) {
+    using namespace hvlm;
+    if (!A || !w_qkv || !qkv_hm || n_frames <= 0) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(qkv_hm) || (b_qkv && !aligned16(b_qkv))) return HVLM_ERR_ALIGN;
+    EpiArgs ep;
+    ep.bias = b_qkv;
+    ep.out = qkv_hm;
+    StageTimer st(HVLM_STAGE_QKV_GEMM, static_cast<cudaStream_t>(stream));
+    return launch_gemm(EPI_QKV_HM, A, w_qkv, n_frames * HVLM_VIT_TOKENS, 3072, 1024, ep, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
                                 int n_frames, float* hidden, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace hvlm;
@@ -118,7 +132,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
     }
     {
         StageTimer st(HVLM_STAGE_LAYERNORM, s);
-        rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s);
+        rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1);
     }
     if (rc) return rc;
 
@@ -126,7 +140,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
         const auto& y = L.layer[l];
         {
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
-            rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+            rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 0);
         }
         if (rc) return rc;
         {
@@ -134,7 +148,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
             ep.bias = f32(y.b_qkv);
             ep.out = w8 + ws.qkv;
             StageTimer st(HVLM_STAGE_QKV_GEMM, s);
-            rc = launch_gemm(EPI_BIAS_BF16, w8 + ws.y, wb + y.w_qkv, M, 3072, 1024, ep, s);
+            rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + y.w_qkv, M, 3072, 1024, ep, s);
             if (rc) return rc;
         }
         {
@@ -153,7 +167,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
         }
         {
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
-            rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s);
+            rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 1);
         }
         if (rc) return rc;
         {
@@ -169,6 +183,7 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
             ep.bias = f32(y.b_fc2);
             ep.resid = hidden;
             ep.out = hidden;
+            ep.reverse = 1;   // fc1 wrote f1 first-to-last: its tail is what L2 still holds
             StageTimer st(HVLM_STAGE_FC2_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.f1, wb + y.w_fc2, M, 1024, 4096, ep, s);
             if (rc) return rc;

@@ -15,9 +15,10 @@ namespace hvlm {
 template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
-                                                            int rows, float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+                                                            int rows, float eps, int reverse) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (reverse) row = rows - 1 - row;   // start with the rows the producer kernel touched last (still in L2)
     const int lane = threadIdx.x & 31;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 1024);
     float4 v[8];
@@ -65,12 +66,12 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s) {
+                     cudaStream_t s, int reverse) {
     const int grid = (rows + 7) / 8;
     if (out_dtype == HVLM_F32)
-        layernorm1024_kernel<float><<<grid, 256, 0, s>>>(x, g, b, static_cast<float*>(out), rows, eps);
+        layernorm1024_kernel<float><<<grid, 256, 0, s>>>(x, g, b, static_cast<float*>(out), rows, eps, reverse);
     else if (out_dtype == HVLM_BF16)
-        layernorm1024_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps);
+        layernorm1024_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps, reverse);
     else
         return HVLM_ERR_BAD_DTYPE;
     return check_last("layernorm");
@@ -198,7 +199,7 @@ extern "C" int hvlm_layernorm_1024(const float* x, const float* gamma, const flo
     using namespace hvlm;
     if (!x || !gamma || !beta || !out || rows <= 0) return HVLM_ERR_BAD_ARG;
     if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(out)) return HVLM_ERR_ALIGN;
-    return launch_layernorm(x, gamma, beta, out, rows, out_dtype, eps, static_cast<cudaStream_t>(stream));
+    return launch_layernorm(x, gamma, beta, out, rows, out_dtype, eps, static_cast<cudaStream_t>(stream), 0);
 }
 
 extern "C" int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls,

@@ -197,13 +197,26 @@ def layernorm_1024(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, out_dtype=
     return out
 
 
-def vit_attention(qkv: torch.Tensor, n_frames: int) -> torch.Tensor:
-    """qkv bf16 [n_frames*257, 3072] (q|k|v, q pre-scaled) -> bf16 [n_frames*257, 1024]."""
-    _need_cuda(qkv)
+def vit_qkv(y: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """y bf16 [M=n_frames*257,1024] -> qkv column-block-major bf16 [48, M, 64] (q0..15|k0..15|v0..15)."""
+    _need_cuda(y, w_qkv, b_qkv)
     ensure_device()
-    assert qkv.dtype == torch.bfloat16 and tuple(qkv.shape) == (n_frames * 257, 3072) and qkv.is_contiguous()
-    out = torch.empty(n_frames * 257, 1024, dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.lib().hvlm_vit_attention(_p(qkv), _p(out), n_frames, _stream()), "hvlm_vit_attention")
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (n_frames * 257, 1024)
+    out = torch.empty(48, n_frames * 257, 64, dtype=torch.bfloat16, device=y.device)
+    L.check(L.lib().hvlm_vit_qkv_gemm(_p(y.contiguous()), _p(w_qkv.contiguous()), _p(b_qkv), _p(out), n_frames, _stream()),
+            "hvlm_vit_qkv_gemm")
+    return out
+
+
+def vit_attention(qkv_hm: torch.Tensor) -> torch.Tensor:
+    """qkv column-block-major bf16 [48, n_frames*257, 64] (q pre-scaled) -> bf16 [n_frames*257, 1024]."""
+    _need_cuda(qkv_hm)
+    ensure_device()
+    assert qkv_hm.dtype == torch.bfloat16 and qkv_hm.dim() == 3 and qkv_hm.shape[0] == 48 and qkv_hm.shape[2] == 64
+    assert qkv_hm.shape[1] % 257 == 0 and qkv_hm.is_contiguous()
+    n_frames = qkv_hm.shape[1] // 257
+    out = torch.empty(n_frames * 257, 1024, dtype=torch.bfloat16, device=qkv_hm.device)
+    L.check(L.lib().hvlm_vit_attention(_p(qkv_hm), _p(out), n_frames, _stream()), "hvlm_vit_attention")
     return out
 
 

@@ -145,9 +145,13 @@ HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames,
 /* building blocks of the tower, exported for per-stage parity tests */
 HVLM_API int hvlm_layernorm_1024(const float* x, const float* gamma, const float* beta, void* out, int rows, int out_dtype,
                         float eps, void* stream);
-/* qkv bf16 [n_frames*257, 3072] = LN1(x) W_qkv^T + b (columns q | k | v, 16 heads x 64 each; q carries the
- * 64^-1/2 scale) -> out bf16 [n_frames*257, 1024] = concat_heads(softmax(q k^T) v).  Heads are read in place by TMA. */
-HVLM_API int hvlm_vit_attention(const void* qkv, void* out, int n_frames, void* stream);
+/* y bf16 [M = n_frames*257, 1024] (LN1 output) -> qkv bf16 COLUMN-BLOCK-MAJOR [48][M][64]: column blocks
+ * q0..q15 | k0..k15 | v0..v15 of (y W_qkv^T + b); q carries the 64^-1/2 scale (folded into the packed weights).
+ * Every (frame, head) operand is a contiguous [257][64] block. */
+HVLM_API int hvlm_vit_qkv_gemm(const void* y, const void* w_qkv, const float* b_qkv, void* qkv_hm, int n_frames,
+                               void* stream);
+/* qkv_hm (layout above) -> out bf16 [n_frames*257, 1024] = concat_heads(softmax(q k^T) v). */
+HVLM_API int hvlm_vit_attention(const void* qkv_hm, void* out, int n_frames, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LITA slow-fast token pooling -- replaces

@@ -306,19 +306,24 @@ def test_splice_backward_matches_oracle():
 
 # ------------------------------------------------------------------ ViT stages
 def test_qkv_and_attention_stage():
-    F = 3
-    y = synth.gen("attn.y", (F * 257, 1024), 1.0, 1).to(torch.bfloat16)
-    w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
-    b = synth.gen("attn.b", (3072,), 0.1, 1)
-    qkv = ops.gemm(y.to(DEV), w.to(DEV), b.to(DEV))
-    assert relmax(qkv, y.float() @ w.float().t() + b) <= 5e-3
-    for scale in (0.125, 1.0):
-        q2 = qkv.clone()
-        q2[:, :1024] = (q2[:, :1024].float() * scale).to(torch.bfloat16)
-        o = ops.vit_attention(q2, F)
-        t = q2.float().cpu().reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)
-        oref = (torch.softmax(t[0] @ t[1].transpose(-1, -2), -1) @ t[2]).permute(0, 2, 1, 3).reshape(F * 257, 1024)
-        assert relmax(o, oref) <= 8e-3
+    """QKV GEMM with the column-block-major epilogue (3-D TMA stores) + attention (tensor-core
+    256x256 block, CUDA-core 257th key / query) against fp32 torch."""
+    for F in (1, 3, 7):
+        y = synth.gen("attn.y", (F * 257, 1024), 1.0, F).to(torch.bfloat16)
+        w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
+        b = synth.gen("attn.b", (3072,), 0.1, 1)
+        qkv = ops.vit_qkv(y.to(DEV), w.to(DEV), b.to(DEV), F)
+        ref = (y.float() @ w.float().t() + b).reshape(F * 257, 48, 64).permute(1, 0, 2)     # [48, M, 64]
+        assert qkv.shape == (48, F * 257, 64) and relmax(qkv, ref) <= 5e-3
+        for scale in (0.125, 1.0):
+            q2 = qkv.clone()
+            q2[:16] = (q2[:16].float() * scale).to(torch.bfloat16)
+            o = ops.vit_attention(q2)
+            t = q2.float().cpu().reshape(3, 16, F, 257, 64)
+            oref = (torch.softmax(t[0] @ t[1].transpose(-1, -2), -1) @ t[2]).permute(1, 2, 0, 3).reshape(F * 257, 1024)
+            assert relmax(o, oref) <= 8e-3
+            # the CUDA-core paths: last query row of every frame, and sensitivity to the last key
+            assert relmax(o.reshape(F, 257, 1024)[:, 256], oref.reshape(F, 257, 1024)[:, 256]) <= 8e-3
 
 
 @pytest.fixture(scope="module")

@@ -133,10 +133,25 @@ def _attn_ref(q, k, v):
     return torch.softmax(s, -1) @ v
 
 
-def _attn_ref_from_qkv(qkv, F):
-    t = qkv.float().cpu().reshape(F, 257, 3, 16, 64).permute(2, 0, 3, 1, 4)   # [3,F,16,257,64]
-    s = t[0] @ t[1].transpose(-1, -2)
-    return (torch.softmax(s, -1) @ t[2]).permute(0, 2, 1, 3).reshape(F * 257, 1024)
+def _attn_ref_from_qkv(qkv_hm):
+    """qkv [48, F*257, 64] -> [F*257,1024] fp32 reference."""
+    F = qkv_hm.shape[1] // 257
+    t = qkv_hm.float().cpu().reshape(3, 16, F, 257, 64)
+    s = t[0] @ t[1].transpose(-1, -2)                                   # [16,F,257,257]
+    return (torch.softmax(s, -1) @ t[2]).permute(1, 2, 0, 3).reshape(F * 257, 1024)
+
+
+def _time(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
 
 
 def stage_attn():
@@ -145,30 +160,26 @@ def stage_attn():
     w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
     w[:1024] *= 0.125
     b = synth.gen("attn.b", (3072,), 0.1, 1)
-    qkv = ops.gemm(y.to(dev), w.to(dev), b.to(dev))
-    stats("qkv_gemm", qkv, y.float() @ w.float().t() + b)
-    stats("attention", ops.vit_attention(qkv, F), _attn_ref_from_qkv(qkv, F))
+    qkv = ops.vit_qkv(y.to(dev), w.to(dev), b.to(dev), F)
+    ref = (y.float() @ w.float().t() + b).reshape(F * 257, 48, 64).permute(1, 0, 2)
+    stats("qkv_gemm_cb_major", qkv, ref)
+    stats("attention", ops.vit_attention(qkv), _attn_ref_from_qkv(qkv))
     qkv2 = qkv.clone()
-    qkv2[:, :1024] *= 6
-    stats("attention_sharp", ops.vit_attention(qkv2, F), _attn_ref_from_qkv(qkv2, F))
+    qkv2[:16] *= 6
+    stats("attention_sharp", ops.vit_attention(qkv2), _attn_ref_from_qkv(qkv2))
     Fb = 100
-    qb = torch.randn(Fb * 257, 3072, device=dev).to(torch.bfloat16)
-    qb[:, :1024] *= 0.3
-    for _ in range(3):
-        ob = ops.vit_attention(qb, Fb)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        ops.vit_attention(qb, Fb)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    qb = torch.randn(48, Fb * 257, 64, device=dev).to(torch.bfloat16)
+    qb[:16] *= 0.3
+    ob = ops.vit_attention(qb)
+    ms = _time(lambda: ops.vit_attention(qb))
     RES["time_attn_100f"] = dict(ms=ms, tflops=Fb * 16 * 4 * 257 * 257 * 64 / ms / 1e9)
-    print(f"attention 100 frames: {ms:.3f} ms", flush=True)
-    t = qb.reshape(Fb, 257, 3, 16, 64).permute(2, 0, 3, 1, 4).float()
-    stats("attention_big_vs_sdpa", ob.reshape(Fb, 257, 16, 64).permute(0, 2, 1, 3),
+    print(f"attention 100 frames: {ms * 1e3:.1f} us", flush=True)
+    t = qb.reshape(3, 16, Fb, 257, 64).float()
+    stats("attention_big_vs_sdpa", ob.reshape(Fb, 257, 16, 64).permute(2, 0, 1, 3),
           torch.nn.functional.scaled_dot_product_attention(t[0], t[1], t[2], scale=1.0))
+    yb = torch.randn(Fb * 257, 1024, device=dev).to(torch.bfloat16)
+    ms = _time(lambda: ops.vit_qkv(yb, w.to(dev), b.to(dev), Fb))
+    print(f"qkv gemm head-major 100 frames: {ms * 1e3:.1f} us  {2 * 25700 * 3072 * 1024 / ms / 1e9:.0f} TF/s", flush=True)
 
 
 def stage_vit():
@@ -224,11 +235,49 @@ def stage_bench():
     RES["profile"] = {k: dict(ms_per_fwd=t / 3, launches=n // 3) for k, (t, n) in prof.items()}
 
 
+def stage_attn_trace():
+    import ctypes as C
+    from hvlm_b200 import _lib as L
+    lib = L.lib()
+    Fb = 100
+    qb = torch.randn(48, Fb * 257, 64, device=dev).to(torch.bfloat16)
+    qb[:16] *= 0.3
+    out = torch.empty(Fb * 257, 1024, dtype=torch.bfloat16, device=dev)
+    grid = min(Fb * 16, 2 * 148)
+    trace = torch.zeros(grid, 2, 4, 16, dtype=torch.int64, device=dev)
+    fn = lib.hvlm_debug_attention_trace
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int]
+    for _ in range(2):
+        ops.vit_attention(qb)
+    dbg = int(os.environ.get("ATTN_DBG", "0"))
+    rc = fn(qb.data_ptr(), out.data_ptr(), Fb, trace.data_ptr(), torch.cuda.current_stream().cuda_stream, dbg)
+    torch.cuda.synchronize()
+    t = trace.cpu()
+    names_m = ["item start", "qk_full", "T0 o_read ok", "T0 S issued", "T0 p_full", "T0 PV issued", "", "",
+               "T1 o_read ok", "T1 S issued(+qk next)", "T1 p_full", "T1 PV issued", "", "", "v free"]
+    names_s = ["item start", "qk_full", "T0 wait s", "T0 s_full", "T0 pass1 done", "T0 p arrived", "T0 o_full", "T0 o read",
+               "T0 epi done", "T1 wait s", "T1 s_full", "T1 pass1 done", "T1 p arrived", "T1 o_full", "T1 o read", "T1 epi done"]
+    for cta in (0, 1, 150, 295):
+        for role, names in ((0, names_m), (1, names_s)):
+            for it in (1, 2):
+                row = t[cta, role, it]
+                base = int(t[cta, role, it][0])
+                prev = base
+                line = []
+                for i, nm in enumerate(names):
+                    v = int(row[i])
+                    if nm and v:
+                        line.append(f"{nm}:+{v - prev}")
+                        prev = v
+                print(f"cta{cta} {'MMA' if role == 0 else 'SMX'} item{it} total={prev - base}: " + " | ".join(line), flush=True)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
     try:
-        {"simple": stage_simple, "gemm": stage_gemm, "attn": stage_attn, "vit": stage_vit, "bench": stage_bench}[stage]()
+        globals()["stage_" + stage]()
         torch.cuda.synchronize()
     except Exception as e:  # noqa
         import traceback
