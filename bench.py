@@ -97,53 +97,69 @@ def make_prompt(B, seed=0):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / power / throttle reasons DURING the timed region (NVML in a background thread, 5 ms period;
+    falls back to `nvidia-smi -lms` if NVML is unavailable)."""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples = []
+        self._stop = False
+        self._thr = None
+        self._nvml = None
+
+    def _loop(self):
+        nv, h = self._nvml, self._h
+        reasons_api = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                     int(reasons_api(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.idx])
+                except Exception:
+                    phys = self.idx
+            self._h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self._max = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._nvml = nv
+            import threading
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
         except Exception:
-            self.p = None
+            self._nvml = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self._nvml is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 8:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-                pw.append(float(c[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.f.name)
-        if sm:
-            load = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
-            out = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm), "power_w_max": max(pw)}
-        return out
+        self._stop = True
+        self._thr.join(timeout=2)
+        nv = self._nvml
+        if not self.samples:
+            return out
+        pmax = max(p for _, p, _ in self.samples)
+        load = [c for c, p, _ in self.samples if p >= 0.5 * pmax] or [c for c, _, _ in self.samples]
+        bits = 0
+        for _, _, r in self.samples:
+            bits |= r
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": self._max,
+                "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(self.samples),
+                "power_w_max": round(pmax, 1)}
 
 
 # ------------------------------------------------------------------------------------------------

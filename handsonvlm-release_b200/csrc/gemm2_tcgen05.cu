@@ -1,0 +1,356 @@
+// 2-CTA (cta_group::2) persistent tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+ fused epilogue)
+//
+// A CTA pair (cluster of 2 = the two SMs of a TPC) computes one 256 x 256 output tile per step:
+//   * each CTA TMA-loads ITS 128 rows of A and ITS 128 rows of B (half of the N extent) per 64-wide K block
+//     (32 KB per stage instead of 48 KB: the B operand is shared across the pair by the tensor-core datapath, which
+//     is what lifts the shared-memory-bandwidth ceiling of the 1-CTA 128x256 kernel)
+//   * the leader CTA's elected lane issues tcgen05.mma.cta_group::2 (M=256, N=256, K=16): rows 0..127 accumulate
+//     in the leader's TMEM, rows 128..255 in the peer's; tcgen05.commit multicasts the "slot free" /
+//     "accumulator ready" mbarrier arrivals to both CTAs
+//   * both CTAs' TMA loads complete_tx on the LEADER's full barrier (cp.async.bulk.tensor...cta_group::2)
+//   * every CTA runs the same 4-warp epilogue as the 1-CTA kernel on its own 128 x 256 half (TMEM -> registers ->
+//     bias / quick-GELU -> swizzled smem -> TMA store / TMA reduce-add), double-buffered against the next tile's MMAs;
+//     the peer's epilogue threads release the accumulator with remote mbarrier arrivals on the leader
+#include <cstdlib>
+
+#include "gemm_epilogue.cuh"
+#include "hvlm_internal.cuh"
+#include "hvlm_ptx.cuh"
+
+namespace hvlm {
+namespace gemm2 {
+
+constexpr int BM = 128;          // rows per CTA (256 per pair)
+constexpr int BN = 256;          // columns per pair (each CTA loads 128 of them)
+constexpr int BK = 64;
+constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int kStages = 6;
+constexpr int kABytes = BM * BK * 2;            // 16 KB
+constexpr int kBBytes = (BN / 2) * BK * 2;      // 16 KB (this CTA's half of B)
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kStoreBuf = BM * 128;
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBuf + 1024 + 256;
+constexpr int kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are accounted on the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the mbarrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 0x3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {   // whole warp, in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiArgs ep) {
+    static_assert(epi_is_staged<EPI>(), "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * kABytes;
+    uint8_t* smem_c = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * kStoreBuf);
+    uint64_t* full_bar = bars;                       // [kStages]  TMA (both CTAs) -> MMA        (leader's copy is used)
+    uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA                    (multicast to both)
+    uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue               (multicast to both)
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogues of BOTH CTAs -> MMA (leader's copy is used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();         // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int n_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_n = N / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_c);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 256);   // 128 epilogue threads in each CTA of the pair
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // peer barriers are initialised and both TMEM allocations are done
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
+            const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
+            const int m_blk = tile / num_n;
+            const int n_blk = tile - m_blk * num_n;
+            const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+            const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                if (elect_one()) {
+                    // the leader arms its barrier with the bytes of BOTH CTAs; the peer's loads complete on it too
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                    tma_load_2d_2sm(smem_a + stage * kABytes, &tma_a, &full_bar[stage], kb * BK, row_a);
+                    tma_load_2d_2sm(smem_b + stage * kBBytes, &tma_b, &full_bar[stage], kb * BK, row_b);
+                }
+                __syncwarp();
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kABytes));
+                    const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * kBBytes));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_ss_2sm(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                                             idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps (2..5), both CTAs: own 128 x 256 half =====================
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        constexpr bool kF32 = epi_out_f32<EPI>();
+        constexpr int kUnitCols = kF32 ? 32 : 64;
+        constexpr int kUnits = BN / kUnitCols;
+        const int row = q * 32 + lane;
+        const int sw = row & 7;
+        const bool store_warp = (warp == 2);
+        uint32_t ucount = 0;
+        for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
+            const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
+            const int m_blk = tile / num_n;
+            const int n_blk = tile - m_blk * num_n;
+            const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int u = 0; u < kUnits; ++u, ++ucount) {
+                uint8_t* buf = smem_c + (ucount & 1u) * kStoreBuf;
+                uint8_t* brow = buf + row * 128;
+                if (store_warp) {
+                    if (elect_one()) bulk_wait_read<1>();
+                    __syncwarp();
+                }
+                named_bar_sync(1, 128);
+                const int n0 = n_blk * BN + u * kUnitCols;
+#pragma unroll
+                for (int h = 0; h < kUnitCols / 32; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + static_cast<uint32_t>(u * kUnitCols + h * 32), r);
+                    tmem_ld_wait();
+                    float v[32];
+                    epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
+                    if constexpr (kF32) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(brow + ((j ^ sw) << 4)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 w;
+                            w.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                            w.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            w.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                            w.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<uint4*>(brow + (((h * 4 + j) ^ sw) << 4)) = w;
+                        }
+                    }
+                }
+                if (u == kUnits - 1) {
+                    // last TMEM read of this accumulator: release it to the (leader's) MMA warp
+                    tc_fence_before();
+                    if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                    else mbar_arrive_cluster(&tempty_bar[acc], 0);
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (store_warp) {
+                    if (elect_one()) {
+                        if constexpr (EPI == EPI_RESID_F32) {
+                            tma_reduce_add_2d(&tma_c, buf, n0, m0);
+                        } else if constexpr (EPI == EPI_QKV_HM) {
+                            tma_store_3d(&tma_c, buf, 0, m0, n0 >> 6);
+                        } else {
+                            tma_store_2d(&tma_c, buf, n0, m0);
+                        }
+                        bulk_commit();
+                    }
+                    __syncwarp();
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        if (store_warp) {
+            if (elect_one()) bulk_wait<0>();
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();     // nobody exits (or frees TMEM) while the peer may still signal / be signalled
+    if (warp == 1) tmem_dealloc_2sm(tmem_base);
+}
+
+template <int EPI>
+static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
+    CUtensorMap ta, tb, tc;
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+        uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+        uint32_t box[2] = {BK, BM};
+        int rc = make_tmap_bf16(&ta, A, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+        uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+        uint32_t box[2] = {BK, BN / 2};
+        int rc = make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        if (!ep.out || !aligned16(ep.out)) return HVLM_ERR_ALIGN;
+        uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+        int rc;
+        if constexpr (EPI == EPI_QKV_HM) {
+            if (N != 3072) return HVLM_ERR_BAD_SHAPE;
+            rc = make_qkv_hm_tmap(&tc, ep.out, M, BM);
+        } else if constexpr (epi_out_f32<EPI>()) {
+            uint64_t str[1] = {static_cast<uint64_t>(N) * 4};
+            uint32_t box[2] = {32, BM};
+            rc = make_tmap_f32(&tc, ep.out, 2, dims, str, box);
+        } else {
+            uint64_t str[1] = {static_cast<uint64_t>(N) * 2};
+            uint32_t box[2] = {64, BM};
+            rc = make_tmap_bf16(&tc, ep.out, 2, dims, str, box);
+        }
+        if (rc) return rc;
+    }
+    auto kern = gemm2_tcgen05_kernel<EPI>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return HVLM_ERR_CUDA;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    kern<<<2 * pairs, kThreads, kSmemBytes, s>>>(ta, tb, tc, M, N, K, ep);
+    return check_last("gemm2");
+}
+
+}  // namespace gemm2
+
+// returns HVLM_ERR_UNSUPPORTED when this (epilogue, shape) has no 2-CTA instantiation
+int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
+    using namespace gemm2;
+    if ((N % BN) != 0) return HVLM_ERR_UNSUPPORTED;
+    switch (epi) {
+        case EPI_BIAS_BF16: return launch_two<EPI_BIAS_BF16>(A, B, M, N, K, ep, s);
+        case EPI_BIAS_F32: return launch_two<EPI_BIAS_F32>(A, B, M, N, K, ep, s);
+        case EPI_GELU_BF16: return launch_two<EPI_GELU_BF16>(A, B, M, N, K, ep, s);
+        case EPI_GELU_F32: return launch_two<EPI_GELU_F32>(A, B, M, N, K, ep, s);
+        case EPI_RESID_F32: return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
+        case EPI_QKV_HM: return launch_two<EPI_QKV_HM>(A, B, M, N, K, ep, s);
+        default: return HVLM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace hvlm

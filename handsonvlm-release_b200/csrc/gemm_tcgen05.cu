@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <mutex>
 
+#include "gemm_epilogue.cuh"
 #include "hvlm_internal.cuh"
 #include "hvlm_ptx.cuh"
 
@@ -106,46 +107,6 @@ struct GemmCfg {
     static constexpr int kStoreBuf = BM * 128;   // one staging unit: 128 rows x 128 B (SWIZZLE_128B box)
     static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBuf + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-__device__ __forceinline__ float quick_gelu(float x) {
-    // x * sigmoid(1.702 x)  (HF QuickGELUActivation); sigmoid(z) = 0.5 tanh(z/2) + 0.5 -> one MUFU op, no divide
-    const float hx = 0.5f * x;
-    return fmaf(hx, tanh_approx(0.851f * x), hx);
-}
-
-template <int EPI>
-__host__ __device__ constexpr bool epi_is_staged() {
-    return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_F32 || EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32 ||
-           EPI == EPI_RESID_F32 || EPI == EPI_QKV_HM;
-}
-template <int EPI>
-__host__ __device__ constexpr bool epi_out_f32() {
-    return EPI == EPI_BIAS_F32 || EPI == EPI_GELU_F32 || EPI == EPI_RESID_F32;
-}
-
-// acc (32 fp32 columns of this thread's row) -> +bias -> (quick-GELU) -> v
-template <int EPI>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], const float* __restrict__ bias, int n0,
-                                              float (&v)[32]) {
-    if (bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    }
-    if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-    }
-}
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m, int n0, int M, int N,
@@ -498,10 +459,21 @@ static int launch_one(const void* A, const void* B, int M, int N, int K, const E
     return check_last("gemm");
 }
 
+int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s);
+
 int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     if (!A || !B || M <= 0 || N <= 0 || K <= 0) return HVLM_ERR_BAD_ARG;
     if ((N % 128) != 0 || (K % 8) != 0) return HVLM_ERR_BAD_SHAPE;
     if (!aligned16(A) || !aligned16(B)) return HVLM_ERR_ALIGN;
+    // preferred path: CTA pairs (cta_group::2, 256x256 tiles); HVLM_GEMM_1CTA=1 selects the single-CTA kernel (A/B runs)
+    static const bool force_1cta = []() {
+        const char* e = getenv("HVLM_GEMM_1CTA");
+        return e && e[0] == '1';
+    }();
+    if (!force_1cta) {
+        const int rc2 = launch_gemm_2cta(epi, A, B, M, N, K, ep, s);
+        if (rc2 != HVLM_ERR_UNSUPPORTED) return rc2;
+    }
     const bool wide = (N % 256) == 0;
 #define HVLM_GEMM_CASE(E)                                                         \
     case E:                                                                       \
