@@ -160,6 +160,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();              // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer + MMA issuer =====================
@@ -487,7 +489,11 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
     }
     const int max_ctas = 2 * num_sms();
     const int grid = n_items < max_ctas ? n_items : max_ctas;
-    attn_tcgen05_kernel<<<grid, kThreads, kSmem, s>>>(tq, tt, static_cast<__nv_bfloat16*>(out), n_items, trace);
+    if (launch_pdl(attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt, static_cast<__nv_bfloat16*>(out), n_items,
+                   trace) != cudaSuccess) {
+        cudaGetLastError();
+        return HVLM_ERR_CUDA;
+    }
     return check_last("attention");
 }
 

@@ -129,6 +129,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     cluster_sync_all();     // peer barriers are initialised and both TMEM allocations are done
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();              // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -332,7 +334,10 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    kern<<<2 * pairs, kThreads, kSmemBytes, s>>>(ta, tb, tc, M, N, K, ep);
+    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
+        cudaGetLastError();
+        return HVLM_ERR_CUDA;
+    }
     return check_last("gemm2");
 }
 

@@ -222,6 +222,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();              // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -455,7 +457,10 @@ static int launch_one(const void* A, const void* B, int M, int N, int K, const E
     }
     const int tiles = ((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tb, tc, M, N, K, ep);
+    if (launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
+        cudaGetLastError();
+        return HVLM_ERR_CUDA;
+    }
     return check_last("gemm");
 }
 

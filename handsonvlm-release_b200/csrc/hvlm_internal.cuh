@@ -54,6 +54,26 @@ struct StageTimer {
     cudaStream_t s_;
 };
 
+// Programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor on the stream drains; it
+// runs its prologue (barrier init, TMEM alloc, descriptor prefetch) and then blocks in pdl_wait() until the
+// predecessor has completed and flushed.  Every kernel launched through this helper MUST call pdl_wait() before
+// touching global memory.  Opt-in with HVLM_PDL=1 (it measured slightly slower than plain stream order, see profile.cu).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace hvlm

@@ -4,6 +4,7 @@
 //   * feature_select (drop CLS, cast)            clip_encoder.py:29-37,49
 //   * transpose-to-bf16 and column sums for the projector wgrad / bias grad
 #include "hvlm_internal.cuh"
+#include "hvlm_ptx.cuh"
 #include "hvlm_vec.cuh"
 
 namespace hvlm {
@@ -16,6 +17,8 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
                                                             int rows, float eps, int reverse) {
+    pdl_launch_dependents();
+    pdl_wait();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     if (reverse) row = rows - 1 - row;   // start with the rows the producer kernel touched last (still in L2)
@@ -69,9 +72,10 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
                      cudaStream_t s, int reverse) {
     const int grid = (rows + 7) / 8;
     if (out_dtype == HVLM_F32)
-        layernorm1024_kernel<float><<<grid, 256, 0, s>>>(x, g, b, static_cast<float*>(out), rows, eps, reverse);
+        launch_pdl(layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse);
     else if (out_dtype == HVLM_BF16)
-        layernorm1024_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps, reverse);
+        launch_pdl(layernorm1024_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps,
+                   reverse);
     else
         return HVLM_ERR_BAD_DTYPE;
     return check_last("layernorm");
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TPix* __restrict__ pi
                                                      const float* __restrict__ cls, const float* __restrict__ pos0,
                                                      float* __restrict__ x0) {
     __shared__ float slab[3 * 14 * 224];
+    pdl_launch_dependents();
+    pdl_wait();
     const int gy = blockIdx.x, f = blockIdx.y;
     const TPix* base = pix + static_cast<size_t>(f) * 3 * 224 * 224;
     for (int idx = threadIdx.x; idx < 3 * 14 * 224; idx += 256) {
@@ -125,7 +131,7 @@ int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, cons
                   float* x0, cudaStream_t s) {
     dim3 grid(16, n_frames);
     HVLM_DISPATCH_DTYPE(pix_dtype, TT, {
-        im2col_kernel<TT><<<grid, 256, 0, s>>>(static_cast<const TT*>(pixels), static_cast<__nv_bfloat16*>(A), cls, pos, x0);
+        launch_pdl(im2col_kernel<TT>, grid, dim3(256), 0, s, static_cast<const TT*>(pixels), static_cast<__nv_bfloat16*>(A), cls, pos, x0);
     });
     return check_last("im2col");
 }

@@ -273,6 +273,23 @@ def stage_attn_trace():
                 print(f"cta{cta} {'MMA' if role == 0 else 'SMX'} item{it} total={prev - base}: " + " | ".join(line), flush=True)
 
 
+def stage_gemm_epi():
+    """epilogue cost by variant, ViT shapes"""
+    for (M, N, K) in ((25700, 1024, 1024), (25700, 1024, 4096), (25700, 4096, 1024), (25700, 3072, 1024)):
+        a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        o16 = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        o32 = torch.zeros(M, N, dtype=torch.float32, device=dev)
+        fl = 2 * M * N * K
+        for name, fn in (("bf16 store", lambda: ops.gemm(a, w, bias, out=o16)),
+                         ("bf16 gelu", lambda: ops.gemm(a, w, bias, epilogue="quick_gelu", out=o16)),
+                         ("f32 store", lambda: ops.gemm(a, w, bias, out=o32)),
+                         ("f32 reduce-add", lambda: ops.gemm(a, w, bias, epilogue="residual", resid=o32, out=o32))):
+            ms = _time(fn, 20)
+            print(f"gemm {M}x{N}x{K} {name:16s}: {ms * 1e3:7.1f} us  {fl / ms / 1e9:6.0f} TF/s", flush=True)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
