@@ -81,8 +81,63 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// LayerNorm(1024) of `nrows` consecutive fp32 rows (<= R) by one warp: rows are read with L1-bypassing loads (they
+// were just produced by TMA reduce-adds from other SMs), two-pass fp32 statistics, bf16 output.
+template <int R>
+__device__ __forceinline__ void ln_rows(const float* __restrict__ x, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int nrows,
+                                        int lane) {
+    float4 v[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r < nrows) {
+            const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * 1024);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[r][j] = __ldcg(xr + lane + 32 * j);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r >= nrows) break;
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * (1.0f / 1024.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+            sq += (a * a + b * b) + (c * c + d * d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * (1.0f / 1024.0f) + 1e-5f);
+        const float4* g4 = reinterpret_cast<const float4*>(gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 g = __ldg(g4 + lane + 32 * j);
+            const float4 b = __ldg(b4 + lane + 32 * j);
+            __nv_bfloat162 lo = __floats2bfloat162_rn((v[r][j].x - mean) * rstd * g.x + b.x, (v[r][j].y - mean) * rstd * g.y + b.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn((v[r][j].z - mean) * rstd * g.z + b.z, (v[r][j].w - mean) * rstd * g.w + b.w);
+            uint2 w;
+            w.x = *reinterpret_cast<uint32_t*>(&lo);
+            w.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(out + static_cast<size_t>(r) * 1024 + (lane + 32 * j) * 4) = w;
+        }
+    }
+}
+
+template <int EPI, bool LN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + (LN ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiArgs ep) {
     static_assert(epi_is_staged<EPI>(), "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
@@ -194,7 +249,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 }
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===================== epilogue warps (2..5), both CTAs: own 128 x 256 half =====================
         const int q = warp & 3;
         int acc = 0;
@@ -206,6 +261,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const int sw = row & 7;
         const bool store_warp = (warp == 2);
         uint32_t ucount = 0;
+        int pending_rb = -1;
         for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
             const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
             const int m_blk = tile / num_n;
@@ -270,14 +326,63 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     __syncwarp();
                 }
             }
+            if constexpr (LN) {
+                // publish the PREVIOUS tile's row block: its reduce-adds are complete once at most this tile's
+                // kUnits groups are still pending (keeps the store pipeline running)
+                if (store_warp) {
+                    if (elect_one()) {
+                        bulk_wait<kUnits>();
+                        if (pending_rb >= 0) {
+                            __threadfence();
+                            atomicAdd(ep.ln_count + pending_rb, 1);
+                        }
+                    }
+                    __syncwarp();
+                }
+                pending_rb = (m0 < M) ? (m0 / BM) : -1;
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1u;
             }
         }
         if (store_warp) {
-            if (elect_one()) bulk_wait<0>();
+            if (elect_one()) {
+                bulk_wait<0>();
+                if constexpr (LN) {
+                    if (pending_rb >= 0) {
+                        __threadfence();
+                        atomicAdd(ep.ln_count + pending_rb, 1);
+                    }
+                }
+            }
             __syncwarp();
+        }
+    } else {
+        // ===================== LayerNorm warps (6..9), only when LN: normalise finished 128-row blocks =====================
+        if constexpr (LN) {
+            const int lw = warp - 6;
+            const int num_rb = (M + BM - 1) / BM;
+            const float* hidden = static_cast<const float*>(ep.out);
+            __nv_bfloat16* y = static_cast<__nv_bfloat16*>(ep.ln_out);
+            for (int i = blockIdx.x; i < num_rb; i += gridDim.x) {
+                const int rb = ep.reverse ? num_rb - 1 - i : i;     // same direction as the tile traversal
+                if (lane == 0) {
+                    while (ld_acquire_gpu(ep.ln_count + rb) < num_n) __nanosleep(256);
+                }
+                __syncwarp();
+                const int r0 = rb * BM + lw * 32;
+#pragma unroll 1
+                for (int r = 0; r < 32; r += 2) {
+                    const int row = r0 + r;
+                    const int nrows = min(2, M - row);
+                    if (nrows > 0)
+                        ln_rows<2>(hidden + static_cast<size_t>(row) * 1024, ep.ln_gamma, ep.ln_beta,
+                                   y + static_cast<size_t>(row) * 1024, nrows, lane);
+                }
+                named_bar_sync(3, 128);
+                if (lw == 0 && lane == 0) ep.ln_count[rb] = 0;     // leave the counters clean for the next launch
+            }
         }
     }
 
@@ -287,7 +392,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (warp == 1) tmem_dealloc_2sm(tmem_base);
 }
 
-template <int EPI>
+template <int EPI, bool LN = false>
 static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     CUtensorMap ta, tb, tc;
     {
@@ -322,7 +427,7 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         }
         if (rc) return rc;
     }
-    auto kern = gemm2_tcgen05_kernel<EPI>;
+    auto kern = gemm2_tcgen05_kernel<EPI, LN>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -334,7 +439,7 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
+    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + (LN ? 128 : 0)), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
     }
@@ -352,7 +457,12 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
         case EPI_BIAS_F32: return launch_two<EPI_BIAS_F32>(A, B, M, N, K, ep, s);
         case EPI_GELU_BF16: return launch_two<EPI_GELU_BF16>(A, B, M, N, K, ep, s);
         case EPI_GELU_F32: return launch_two<EPI_GELU_F32>(A, B, M, N, K, ep, s);
-        case EPI_RESID_F32: return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
+        case EPI_RESID_F32:
+            if (ep.ln_out != nullptr) {
+                if (N != 1024 || !ep.ln_gamma || !ep.ln_beta || !ep.ln_count) return HVLM_ERR_BAD_ARG;
+                return launch_two<EPI_RESID_F32, true>(A, B, M, N, K, ep, s);
+            }
+            return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
         case EPI_QKV_HM: return launch_two<EPI_QKV_HM>(A, B, M, N, K, ep, s);
         default: return HVLM_ERR_UNSUPPORTED;
     }

@@ -28,6 +28,12 @@ struct EpiArgs {
     void* out = nullptr;
     const float* pos = nullptr;
     int reverse = 0;   // walk the tiles last-to-first (start with what the producer kernel left in L2)
+    // fused LayerNorm of the updated residual rows (EPI_RESID_F32, N == 1024, 2-CTA kernel only): extra warps
+    // normalise each 128-row block as soon as all of its column tiles have been reduced into `out`
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    void* ln_out = nullptr;        // bf16 [M,1024]
+    int32_t* ln_count = nullptr;   // int32 [ceil(M/128)], zero on entry, zero again on exit
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue.  Returns an hvlm_status.

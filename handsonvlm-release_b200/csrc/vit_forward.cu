@@ -21,7 +21,7 @@ int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct VitWorkspace {
-    uint64_t a_patch, y, qkv, attn, f1, total;
+    uint64_t a_patch, y, qkv, attn, f1, ln_count, total;
 };
 
 static VitWorkspace vit_workspace(int n_frames) {
@@ -39,6 +39,7 @@ static VitWorkspace vit_workspace(int n_frames) {
     w.qkv = take(M * 3072 * 2);
     w.attn = take(M * 1024 * 2);
     w.f1 = take(M * 4096 * 2);
+    w.ln_count = take(((M + 127) / 128) * 4);
     w.total = off;
     return w;
 }
@@ -116,6 +117,17 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
     auto f32 = [&](uint64_t off) { return reinterpret_cast<const float*>(wb + off); };
     const int M = n_frames * HVLM_VIT_TOKENS;
 
+    // Experimental (HVLM_LN_FUSION=1): LayerNorm fused into the residual GEMMs (extra warps normalise each 128-row block
+    // as soon as its column tiles are reduced).  Correct, but measured SLOWER on B200 (15.75 vs 15.20 ms per 100 frames):
+    // the in-kernel LN warps are L2-latency-bound (2 rows in flight per warp) while the stand-alone LN kernel already
+    // streams at ~5 TB/s, so the separate kernels stay the default.
+    static const bool fuse_ln = []() {
+        const char* e = getenv("HVLM_LN_FUSION");
+        return e && e[0] == '1';
+    }();
+    int32_t* ln_count = reinterpret_cast<int32_t*>(w8 + ws.ln_count);
+    if (fuse_ln && cudaMemsetAsync(ln_count, 0, static_cast<size_t>((M + 127) / 128) * 4, s) != cudaSuccess) return HVLM_ERR_CUDA;
+
     // embeddings: im2col (+ CLS rows) -> patch GEMM (+ position embedding) -> pre_layrnorm (in place)
     {
         StageTimer st(HVLM_STAGE_IM2COL, s);
@@ -138,11 +150,11 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
 
     for (int l = 0; l < n_layers_run; ++l) {
         const auto& y = L.layer[l];
-        {
+        if (!fuse_ln || l == 0) {   // with fusion, LN1 of layer l > 0 was produced by fc2 of layer l-1
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 0);
+            if (rc) return rc;
         }
-        if (rc) return rc;
         {
             EpiArgs ep;
             ep.bias = f32(y.b_qkv);
@@ -161,15 +173,21 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
             ep.bias = f32(y.b_o);
             ep.resid = hidden;
             ep.out = hidden;
+            if (fuse_ln) {   // LN2 fused: y = LN2(hidden) is produced as row blocks complete
+                ep.ln_gamma = f32(y.ln2_g);
+                ep.ln_beta = f32(y.ln2_b);
+                ep.ln_out = w8 + ws.y;
+                ep.ln_count = ln_count;
+            }
             StageTimer st(HVLM_STAGE_OUTPROJ_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.attn, wb + y.w_o, M, 1024, 1024, ep, s);
             if (rc) return rc;
         }
-        {
+        if (!fuse_ln) {
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 1);
+            if (rc) return rc;
         }
-        if (rc) return rc;
         {
             EpiArgs ep;
             ep.bias = f32(y.b_fc1);
@@ -184,6 +202,12 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
             ep.resid = hidden;
             ep.out = hidden;
             ep.reverse = 1;   // fc1 wrote f1 first-to-last: its tail is what L2 still holds
+            if (fuse_ln && l + 1 < n_layers_run) {   // LN1 of the next layer fused into this GEMM
+                ep.ln_gamma = f32(L.layer[l + 1].ln1_g);
+                ep.ln_beta = f32(L.layer[l + 1].ln1_b);
+                ep.ln_out = w8 + ws.y;
+                ep.ln_count = ln_count;
+            }
             StageTimer st(HVLM_STAGE_FC2_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.f1, wb + y.w_fc2, M, 1024, 4096, ep, s);
             if (rc) return rc;
