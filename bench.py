@@ -221,6 +221,49 @@ def traffic_for(kernel):
         return None
 
 
+def _time_events(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def hbm_stage_rooflines(dev, pk):
+    """The HBM-bound stages at sizes larger than L2 (north_star asks for >= 70 % of HBM peak on pooling / splice):
+    slow-fast pooling on the reference-order shape (fp32 [1,100,256,4096], 425 MB) and the splice row gather at
+    64 clips (440 MB).  Algorithmic bytes / CUDA-event time of back-to-back launches."""
+    from hvlm_b200 import _lib as L
+    from hvlm_b200 import ops
+    out = {}
+    tok = torch.randn(1, FRAMES, 256, 4096, device=dev)
+    ms = _time_events(lambda: ops.pool_tokens(tok, "temporal_spatial_pool"))
+    by = tok.numel() * 4 + 356 * 4096 * 4
+    out["pool_slowfast_f32_C4096"] = {"bytes": by, "us": round(ms * 1e3, 1), "gbs": round(by / ms / 1e6, 1),
+                                      "frac_of_hbm_peak": round(by / ms / 1e6 / pk["hbm"], 3)}
+    del tok
+    B, D, T = 64, 4096, 64
+    table = torch.randn(VOCAB, D, device=dev).to(torch.bfloat16)
+    vis = torch.randn(B, 356, D, device=dev).to(torch.bfloat16)
+    ids, mask, labels, fh, _ = make_prompt(B)
+    ids = torch.cat([ids, torch.full((B, T - T_PROMPT), 5, dtype=torch.int64)], 1).to(dev)
+    labels, mask, fh = ids.clone(), torch.ones_like(ids, dtype=torch.bool), fh.to(dev)
+    counts = ops.splice_count(ids)
+    Lout = T - 1 + 356
+    plan = ops.splice_plan(ids, counts, 356, B, Lout, VOCAB, L.SPLICE_HANDSONVLM, 1, 4)
+    ms = _time_events(lambda: ops.splice_gather(plan[0], plan[1], plan[2], plan[3], ids, labels, mask, table, vis, None, fh,
+                                                L.SPLICE_HANDSONVLM))
+    by = B * ((T - 1 + 356) * D * 2 + Lout * (D * 2 + 9))
+    out["splice_gather_B64_D4096"] = {"bytes": by, "us": round(ms * 1e3, 1), "gbs": round(by / ms / 1e6, 1),
+                                      "frac_of_hbm_peak": round(by / ms / 1e6 / pk["hbm"], 3)}
+    return out
+
+
 def run_ours(args):
     from hvlm_b200 import dist as hd
     from hvlm_b200 import ops
@@ -355,7 +398,7 @@ def run_ours(args):
             "model_tflops": round(value * VIT_GFLOP_PER_FRAME / 1e3 / world, 1),
             "roofline": roofline,
             "gemm_aggregate": {"tflops": round(gemm_fl / gemm_ms / 1e9, 1), "ms_per_step": round(gemm_ms, 3)},
-            "stages": stages, "clocks": clk,
+            "stages": stages, "hbm_stages": hbm_stage_rooflines(dev, pk), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             res["cpu_baseline"] = cpu_baseline(sd, D, sample_frames=args.cpu_sample_frames)

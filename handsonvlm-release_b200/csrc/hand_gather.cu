@@ -2,8 +2,8 @@
 //
 // Replaces the per-sample Python loop inside HandsOnVLMForCausalLM.forward
 // (handsonvlm/model/language_model/handsonvlm.py:146-187: bool-mask index + reshape(4,D/2,2).permute(2,0,1),
-// one host sync per sample) and the generation-time gather (:609-622).  One CTA per sample: a block scan over
-// the shifted label mask finds the (up to) 4 predictor rows, then the rows are copied with the even/odd channel
+// one host sync per sample) and the generation-time gather (:609-622).  Four CTAs per sample: a block scan over
+// the shifted label mask finds the (up to) 4 predictor rows, CTA k copies row k with the even/odd channel
 // de-interleave  out[b,h,k,j] = hidden[b,row_k,2j+h].  No host sync; counts[] lets the caller enforce the
 // reference's "0 or 4" contract.
 #include "hvlm_internal.cuh"
@@ -12,6 +12,8 @@
 
 namespace hvlm {
 
+// grid = (B, 4): every CTA scans its sample's labels (cheap), CTA (b,k) then copies predictor row k with 16-byte
+// vector loads, de-interleaving even/odd channels in registers.
 template <typename T>
 __global__ void __launch_bounds__(kPlanThreads)
 hand_gather_fwd_kernel(const T* __restrict__ hidden, const int64_t* __restrict__ labels, int64_t hand_id, int L, int D,
@@ -20,6 +22,7 @@ hand_gather_fwd_kernel(const T* __restrict__ hidden, const int64_t* __restrict__
     __shared__ int scan_smem[9];
     __shared__ int srow[4];
     const int b = blockIdx.x;
+    const int k = blockIdx.y;
     const int64_t* lab = labels + static_cast<int64_t>(b) * L;
     if (threadIdx.x < 4) srow[threadIdx.x] = -1;
     int seen = 0;
@@ -33,26 +36,43 @@ hand_gather_fwd_kernel(const T* __restrict__ hidden, const int64_t* __restrict__
         seen += total;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        counts[b] = seen;
-        valid[b] = seen > 0;
-    }
-    if (threadIdx.x < 4) rows[b * 4 + threadIdx.x] = srow[threadIdx.x];
-    const int half = D >> 1;
-    // thread handles channel pairs: hidden[row, 2j], hidden[row, 2j+1] -> out[b,0,k,j], out[b,1,k,j]
-    for (int idx = threadIdx.x; idx < 4 * half; idx += blockDim.x) {
-        const int k = idx / half;
-        const int j = idx - k * half;
-        const int r = srow[k];
-        T e = from_float<T>(0.f), o = from_float<T>(0.f);
-        if (r >= 0) {
-            const T* src = hidden + (static_cast<int64_t>(b) * L + r) * D + 2 * j;
-            e = src[0];
-            o = src[1];
+    if (k == 0) {
+        if (threadIdx.x == 0) {
+            counts[b] = seen;
+            valid[b] = seen > 0;
         }
-        T* dst = out + static_cast<int64_t>(b) * 2 * 4 * half;
-        dst[(0 * 4 + k) * half + j] = e;
-        dst[(1 * 4 + k) * half + j] = o;
+        if (threadIdx.x < 4) rows[b * 4 + threadIdx.x] = srow[threadIdx.x];
+    }
+    const int half = D >> 1;
+    const int r = srow[k];
+    T* dst_e = out + ((static_cast<int64_t>(b) * 2 + 0) * 4 + k) * half;
+    T* dst_o = out + ((static_cast<int64_t>(b) * 2 + 1) * 4 + k) * half;
+    const T* src = hidden + (static_cast<int64_t>(b) * L + (r >= 0 ? r : 0)) * D;
+    constexpr int V = 16 / sizeof(T);                  // elements per 16-byte vector
+    if ((D % (2 * V)) == 0 && (reinterpret_cast<uintptr_t>(hidden) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        // two input vectors (2V elements = V pairs) -> one even vector + one odd vector
+        for (int p = threadIdx.x * V; p < half; p += blockDim.x * V) {
+            T in[2 * V], ev[V], od[V];
+            if (r >= 0) {
+                *reinterpret_cast<uint4*>(&in[0]) = *reinterpret_cast<const uint4*>(src + 2 * p);
+                *reinterpret_cast<uint4*>(&in[V]) = *reinterpret_cast<const uint4*>(src + 2 * p + V);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2 * V; ++i) in[i] = from_float<T>(0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                ev[i] = in[2 * i];
+                od[i] = in[2 * i + 1];
+            }
+            *reinterpret_cast<uint4*>(dst_e + p) = *reinterpret_cast<uint4*>(&ev[0]);
+            *reinterpret_cast<uint4*>(dst_o + p) = *reinterpret_cast<uint4*>(&od[0]);
+        }
+    } else {
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            dst_e[j] = r >= 0 ? src[2 * j] : from_float<T>(0.f);
+            dst_o[j] = r >= 0 ? src[2 * j + 1] : from_float<T>(0.f);
+        }
     }
 }
 
@@ -95,7 +115,7 @@ extern "C" int hvlm_hand_gather_fwd(const void* hidden, int dtype, const int64_t
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     StageTimer st(HVLM_STAGE_GATHER, s);
     HVLM_DISPATCH_DTYPE(dtype, TT, {
-        hand_gather_fwd_kernel<TT><<<B, kPlanThreads, 0, s>>>(static_cast<const TT*>(hidden), labels, hand_id, L, D,
+        hand_gather_fwd_kernel<TT><<<dim3(B, 4), kPlanThreads, 0, s>>>(static_cast<const TT*>(hidden), labels, hand_id, L, D,
                                                              static_cast<TT*>(out), valid, rows, counts);
     });
     return check_last("hand_gather_fwd");

@@ -290,6 +290,63 @@ def stage_gemm_epi():
             print(f"gemm {M}x{N}x{K} {name:16s}: {ms * 1e3:7.1f} us  {fl / ms / 1e9:6.0f} TF/s", flush=True)
 
 
+def stage_hbm():
+    """HBM-bound kernels at sizes larger than L2: achieved GB/s (algorithmic bytes / CUDA-event time)."""
+    from hvlm_b200 import _lib as L
+    # pooling, reference order: fp32 [B,100,256,4096] -> [B,356,4096]
+    for B, C, dt in ((1, 4096, torch.float32), (4, 4096, torch.float32), (4, 4096, torch.bfloat16), (4, 1024, torch.float32)):
+        tok = torch.randn(B, 100, 256, C, device=dev, dtype=dt)
+        ms = _time(lambda: ops.pool_tokens(tok, "temporal_spatial_pool"), 20)
+        by = tok.numel() * tok.element_size() + B * 356 * C * tok.element_size()
+        print(f"pool fwd B={B} C={C} {str(dt)[6:]:8s}: {ms * 1e3:7.1f} us  {by / ms / 1e6:7.0f} GB/s", flush=True)
+    hid = torch.randn(400, 257, 1024, device=dev)
+    ms = _time(lambda: ops.pool_slowfast(hid, 4, 100, 257, 1, 0, True), 20)
+    by = 400 * 256 * 1024 * 4 + 4 * 356 * 1024 * 2
+    print(f"pool fwd in-place hidden layout B=4: {ms * 1e3:7.1f} us  {by / ms / 1e6:7.0f} GB/s", flush=True)
+    dout = torch.randn(4, 356, 4096, device=dev)
+    ms = _time(lambda: ops.pool_slowfast_bwd(dout, 100, 0, False), 20)
+    print(f"pool bwd B=4 C=4096 f32: {ms * 1e3:7.1f} us  {(4 * 100 * 256 * 4096 * 4) / ms / 1e6:7.0f} GB/s (write)", flush=True)
+    # splice
+    for B, D in ((16, 4096), (64, 4096), (16, 5120)):
+        table = torch.randn(32101, D, device=dev).to(torch.bfloat16)
+        vis = torch.randn(B, 356, D, device=dev).to(torch.bfloat16)
+        ids = torch.randint(1, 32000, (B, 64), device=dev)
+        ids[:, 35] = -200
+        ids[:, 56:60] = 32100
+        labels = ids.clone()
+        mask = torch.ones_like(ids, dtype=torch.bool)
+        fh = torch.rand(B, 2, 4, 2, device=dev)
+        counts = ops.splice_count(ids)
+        Lout = 64 - 1 + 356
+        plan = ops.splice_plan(ids, counts, 356, B, Lout, 32101, L.SPLICE_HANDSONVLM, 1, 4)
+        fn = lambda: ops.splice_gather(plan[0], plan[1], plan[2], plan[3], ids, labels, mask, table, vis, None, fh,
+                                       L.SPLICE_HANDSONVLM)
+        hidden = torch.randn(B, Lout, D, device=dev).to(torch.bfloat16)
+        lab2 = fn()[1]
+        big = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ops.profile_enable(True)
+        for _ in range(10):
+            big.zero_()                      # flush L2 between iterations (512 MB write)
+            torch.cuda.synchronize()         # keep host launch latency out of the event pairs
+            fn()
+            ops.hand_gather(hidden, lab2, 32100)
+        prof = ops.profile_collect()
+        ops.profile_enable(False)
+        by = B * ((63 + 356) * D * 2 + Lout * (D * 2 + 9))
+        t, n = prof["splice"]
+        print(f"splice fwd B={B} D={D}: {t / n * 1e3:7.1f} us (device, L2 flushed)  {by / (t / n) / 1e6:7.0f} GB/s", flush=True)
+        t, n = prof["gather"]
+        print(f"hand gather B={B} D={D}: {t / n * 1e3:7.1f} us (device)", flush=True)
+    x = torch.randn(25700, 1024, device=dev)
+    g = torch.ones(1024, device=dev)
+    b = torch.zeros(1024, device=dev)
+    ms = _time(lambda: ops.layernorm_1024(x, g, b), 20)
+    print(f"layernorm 25700 rows: {ms * 1e3:7.1f} us  {25700 * 1024 * 6 / ms / 1e6:7.0f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
     stage = sys.argv[1]
     t0 = time.time()
