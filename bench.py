@@ -322,23 +322,39 @@ def run_ours(args):
     frames_per_step = B * FRAMES * world
     value = frames_per_step / (ms_step / 1e3)
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region, wall clock
-    def e2e_step():
-        pixels = px_host.to(dev, non_blocking=True)
-        ins = [t.to(dev, non_blocking=True) for t in host_in]
-        r, gout = step(pixels, ins)
-        out_host.copy_(gout, non_blocking=True)
-        return r
+    # ---- e2e: host buffers, H2D + D2H inside the timed region, wall clock.  The clip of step i+1 is copied on a side
+    #      stream while step i computes (what a prefetching data loader does); every step's inputs still cross PCIe
+    #      inside the timed region and every step's result is read back to the host.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
 
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
+    def h2d_async():
+        with torch.cuda.stream(copy_stream):
+            pixels = px_host.to(dev, non_blocking=True)
+            ins = [t.to(dev, non_blocking=True) for t in host_in]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return pixels, ins, ev
+
+    def e2e_run(n):
+        nxt = h2d_async()
+        for i in range(n):
+            pixels, ins, ev = nxt
+            if i + 1 < n:
+                nxt = h2d_async()
+            main_stream.wait_event(ev)
+            pixels.record_stream(main_stream)
+            for t in ins:
+                t.record_stream(main_stream)
+            r, gout = step(pixels, ins)
+            out_host.copy_(gout, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_run(2)
     hd.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
+    e2e_run(args.steps)
     e2e_s = hd.max_over_ranks(time.perf_counter() - t0, dev)
     hd.barrier()
     h2d = px_host.numel() * px_host.element_size() + sum(t.numel() * t.element_size() for t in host_in)
@@ -374,7 +390,7 @@ def run_ours(args):
             stages[k] = st
         dom = "fc1_gemm"
         achieved = stages[dom]["tflops"]
-        roofline = {"kernel": "gemm_tcgen05_kernel<256, EPI_GELU_BF16> (ViT fc1: M=%d N=4096 K=1024)" % M,
+        roofline = {"kernel": "gemm2_tcgen05_kernel<EPI_GELU_BF16> (2-CTA tcgen05 GEMM, ViT fc1: M=%d N=4096 K=1024)" % M,
                     "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": round(achieved / pk["tf_sustained"], 4),
                     "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
@@ -404,6 +420,66 @@ def run_ours(args):
             res["cpu_baseline"] = cpu_baseline(sd, D, sample_frames=args.cpu_sample_frames)
     if rank == 0:
         print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args):
+    """Training-shaped variant: fwd through ViT (no grad) + pool/projector/splice/gather with
+    autograd, backward with upstream gradients (pool bwd, projector wgrad/bgrad, splice scatter-add, gather scatter),
+    then ONE NCCL all-reduce of the projector gradients.  4 clips per GPU by default."""
+    from hvlm_b200 import dist as hd
+    from hvlm_b200 import ops
+    import torch.distributed as dist
+
+    rank, world, local = hd.env_rank_world()
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    hd.init_process_group("nccl" if world > 1 else None)
+    ops.ensure_device()
+    D, B = args.hidden, args.clips
+    host = build_host(D, dev, clip_state_dict(23))
+    host.B = B
+    proj, emb = host.model.mm_projector, host.model.embed_tokens
+    ids, mask, labels, fh, fv = [t.to(dev) for t in make_prompt(B, seed=rank)]
+    px = torch.randn(B, FRAMES, 3, 224, 224, device=dev).to(torch.bfloat16)
+    Lout = T_PROMPT + 355
+    de = torch.randn(B, Lout, D, device=dev, dtype=torch.bfloat16)
+    dg = torch.randn(B, 2, 4, D // 2, device=dev, dtype=torch.bfloat16)
+
+    def step():
+        proj.zero_grad(set_to_none=True)
+        emb.zero_grad(set_to_none=True)
+        r = host.prepare_inputs_labels_for_multimodal(ids, mask, None, labels, px, future_hands=fh, future_valid=fv,
+                                                      is_evaluate=False)
+        gout, _ = host.gather_hand_traj_states(r[3], r[4], strict=False)     # embeddings stand in for LLM states
+        torch.autograd.backward([r[3], gout], [de, dg])
+        hd.allreduce_projector_grads(proj)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    hd.barrier()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    hd.barrier()
+    ms = hd.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "video frames/sec visual-token prep, training-shaped (fwd + bwd + projector-grad all-reduce)",
+            "value": round(B * FRAMES * world / (ms / 1e3), 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[4]: training-shaped, %d clips/GPU x 100 frames, D=%d, upstream grads randn, "
+                                   "NCCL all-reduce of mm_projector grads (%d elements)" % (B, D, D * 1024 + D),
+                       "parallelism": f"clip-sharded dp{world}"},
+            "gpu_launches": int(ops.launch_count() - l0)}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -447,7 +523,7 @@ def cpu_baseline(sd, D, sample_frames=8):
         _cpu_path_once(px, sd24, pw, pb, table, ids, mask, labels, fh)
         dt = time.perf_counter() - t0
     return {"value": round(sample_frames / dt, 3), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample_frames}-frame clip (of the 100-frame workload) through the fp32 torch-CPU restatement of the "
+            "sample": f"one {sample_frames}-frame clip (the 100-frame workload is 100 frames) through the fp32 torch-CPU restatement of the "
                       f"reference path (24-layer ViT as executed by the reference, projector on all tokens, pool, splice, "
                       f"gather); {dt:.1f} s"}
 
@@ -491,12 +567,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hidden", type=int, default=4096, help="LLM hidden size D (4096 = 7B, 5120 = 13B)")
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
-    ap.add_argument("--cpu-sample-frames", type=int, default=8)
+    ap.add_argument("--cpu-sample-frames", type=int, default=100)
     ap.add_argument("--cpu-sample-frames-ref", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward = the headline metric; train = training-shaped variant (fwd+bwd+all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        if args.clips == 1:
+            args.clips = 4
+        run_train(args)
     else:
         run_ours(args)
 

@@ -42,6 +42,49 @@ def _project(projector, x2d: torch.Tensor) -> torch.Tensor:
     return y if y.dtype == w.dtype else y.to(w.dtype)
 
 
+class VisualTokenCache:
+    """SURVEY.md section 8(f) item 1.  The reference re-runs the whole visual path for EVERY generated token
+    (``generate(use_cache=False)``: handsonvlm_inference.py:99-109 -> handsonvlm.py:555-564, and HandsOnVLM dropped the
+    ``T == 1`` early-out LLaVA has at llava_arch.py:117-120).  With ``config.hvlm_cache_visual_tokens = True`` the
+    drop-in keeps the visual tokens of the last clip and reuses them while the SAME image tensor (same storage, shape,
+    dtype and version counter, i.e. not modified in place) is passed again under ``torch.no_grad()``: the ViT, pooling
+    and projector then run once per sample instead of once per token.  Off by default (bit-identical either way)."""
+
+    def __init__(self):
+        self.key = None
+        self.value = None
+        self.hits = 0
+
+    @staticmethod
+    def _key(images, extra):
+        return (images.data_ptr(), tuple(images.shape), images.dtype, images.device, images._version, extra)
+
+    def get(self, images, extra):
+        if torch.is_grad_enabled() or self.key is None or self.key != self._key(images, extra):
+            return None
+        self.hits += 1
+        return self.value
+
+    def put(self, images, extra, value):
+        if not torch.is_grad_enabled():
+            self.key, self.value = self._key(images, extra), value
+
+    def clear(self):
+        self.key = self.value = None
+
+
+def _cached_video_tokens(host, tower, projector, images, mode):
+    if not getattr(host.config, "hvlm_cache_visual_tokens", False):
+        return video_tokens(tower, projector, images, mode)
+    cache = host.__dict__.setdefault("_hvlm_visual_cache", VisualTokenCache())
+    extra = (mode, projector.weight.data_ptr(), projector.weight._version, tower.weight_blob.data_ptr())
+    tok = cache.get(images, extra)
+    if tok is None:
+        tok = video_tokens(tower, projector, images, mode)
+        cache.put(images, extra, tok)
+    return tok
+
+
 def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str) -> torch.Tensor:
     """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project)."""
     assert images.ndim == 5, "multiple videos per sample not supported yet"
@@ -68,7 +111,8 @@ class VisualToTokenHelper:
     lmdb features and are out of scope), video_compress_mode in {'temporal_spatial_pool','spatial_pool','none'}."""
 
     def __init__(self, images_raw_encode, images_mm_projector, fuse_input_mode, video_compress_mode,
-                 mm_hidden_size, token_dim):
+                 mm_hidden_size, token_dim, cache_host=None):
+        self.cache_host = cache_host          # optional: object whose config enables the visual-token cache
         self.images_raw_encode = images_raw_encode
         self.images_mm_projector = images_mm_projector
         self.fuse_input_mode = fuse_input_mode
@@ -86,7 +130,11 @@ class VisualToTokenHelper:
         if self.video_compress_mode not in ("temporal_spatial_pool", "spatial_pool", "none"):
             raise ValueError(f"unsupported video_compress_mode: {self.video_compress_mode}")
         self.b, self.t, self.c, self.h, self.w = images.shape
-        out = video_tokens(self.images_raw_encode, self.images_mm_projector, images, self.video_compress_mode)
+        if self.cache_host is not None:
+            out = _cached_video_tokens(self.cache_host, self.images_raw_encode, self.images_mm_projector, images,
+                                       self.video_compress_mode)
+        else:
+            out = video_tokens(self.images_raw_encode, self.images_mm_projector, images, self.video_compress_mode)
         n = out.shape[1]
         assert out.shape == torch.Size([self.b, n, self.token_dim]), \
             f"output_tokens.shape = {out.shape}, expected shape is {torch.Size([self.b, n, self.token_dim])}"
@@ -230,7 +278,8 @@ class LitaMetaForCausalLM(LlavaMetaForCausalLM):
     def videos_to_tokens(self, images):
         assert images.ndim == 5, "multiple videos per sample not supported yet"
         video_arch = getattr(self.config, "video_arch", "temporal")
-        return video_tokens(self.get_model().get_vision_tower(), self.get_model().mm_projector, images, video_arch)
+        return _cached_video_tokens(self, self.get_model().get_vision_tower(), self.get_model().mm_projector, images,
+                                    video_arch)
 
     def visual_to_tokens(self, images):
         input_type = getattr(self.config, "input_type", "image")
@@ -272,7 +321,8 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
                                      images_mm_projector=self.get_model().mm_projector,
                                      fuse_input_mode=self.config.fuse_input_mode,
                                      video_compress_mode=self.config.video_compress_mode,
-                                     mm_hidden_size=self.config.mm_hidden_size, token_dim=self.token_dim)
+                                     mm_hidden_size=self.config.mm_hidden_size, token_dim=self.token_dim,
+                                     cache_host=self)
         visual_tokens, visual_mask = helper.pipeline(images=images, **kwargs)
         assert visual_tokens.shape == torch.Size([self.B, visual_tokens.shape[1], self.token_dim]), visual_tokens.shape
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
@@ -284,6 +334,11 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
         is_img = input_ids[-1] == IMAGE_TOKEN_INDEX
         self.last_visual_token_index = is_img.to(torch.int32).argmax() + visual_tokens.shape[1]
         return None, new_mask, past_key_values, embeds, new_labels
+
+    def clear_visual_token_cache(self):
+        cache = self.__dict__.get("_hvlm_visual_cache")
+        if cache is not None:
+            cache.clear()
 
     def gather_hand_traj_states(self, hidden_states, labels, future_valid=None, strict=True):
         return gather_hand_traj_states(hidden_states, labels, HAND_TRAJ_TOKEN_ID, future_valid, strict)

@@ -495,3 +495,40 @@ def test_training_shaped_backward(tower23):
     pw, pb = host.model.mm_projector.weight, host.model.mm_projector.bias
     assert relmax(pw.grad, dW) <= TOL_BF16 and relmax(pb.grad, db) <= 1e-4
     assert relmax(host.model.embed_tokens.weight.grad, d_tab) <= 1e-5
+
+
+def test_visual_token_cache_for_generation(tower23):
+    """with config.hvlm_cache_visual_tokens the ViT/pool/projector run once per clip, not once per
+    generated token; results are bit-identical and an in-place change of the clip invalidates the cache."""
+    tw, sd = tower23("hf")
+    D, t = 256, 4
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    cfg = types.SimpleNamespace(fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool", mm_hidden_size=1024,
+                                input_type="video", hvlm_cache_visual_tokens=True)
+    host = _host(arch.HandsOnVLMMetaForCausalLM, tw, proj, emb, cfg, 1)
+    px = synth.pixels((1, t, 3, 224, 224), seed=5).to(DEV)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=1, seed=5)
+    args = (ids.to(DEV), mask.to(DEV), None, None, px)
+    with torch.no_grad():
+        n0 = ops.launch_count()
+        r1 = host.prepare_inputs_labels_for_multimodal(*args, is_evaluate=True)
+        n1 = ops.launch_count()
+        # "next token": one more id appended, same clip tensor -> cache hit, no tower launches
+        ids2 = torch.cat([ids, torch.tensor([[7]])], 1).to(DEV)
+        m2 = torch.ones_like(ids2, dtype=torch.bool)
+        r2 = host.prepare_inputs_labels_for_multimodal(ids2, m2, None, None, px, is_evaluate=True)
+        n2 = ops.launch_count()
+        assert n1 - n0 > 30 and n2 - n1 <= 4
+        assert torch.equal(r2[3][:, : r1[3].shape[1]], r1[3])
+        px.add_(0.0)                                   # in-place touch bumps the version counter -> recompute
+        host.prepare_inputs_labels_for_multimodal(*args, is_evaluate=True)
+        assert ops.launch_count() - n2 > 30
+    # never cached when autograd is recording
+    host.clear_visual_token_cache()
+    r3 = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px,
+                                                   future_hands=fh.to(DEV), future_valid=fv.to(DEV))
+    assert host.__dict__["_hvlm_visual_cache"].key is None and r3[3].requires_grad
