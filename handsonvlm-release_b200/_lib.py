@@ -48,6 +48,7 @@ SIGNATURES = {
     "hvlm_vit_l14_layout": (i32, [i32, C.POINTER(VitLayout)]),
     "hvlm_vit_l14_workspace_bytes": (sz, [i32]),
     "hvlm_vit_l14_fwd": (i32, [p, i32, p, i32, i32, p, p, sz, p]),
+    "hvlm_vit_l14_fwd_u8": (i32, [p, i32, p, C.POINTER(f32), C.POINTER(f32), i32, p, p, sz, p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
     "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, i32, p]),

@@ -89,7 +89,7 @@ def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: 
     """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project)."""
     assert images.ndim == 5, "multiple videos per sample not supported yet"
     b, t = images.shape[:2]
-    flat = images.reshape(b * t, *images.shape[2:])
+    flat = images.reshape(b * t, *images.shape[2:])      # [b*t,3,224,224] float, or raw uint8 [b*t,224,224,3]
     with torch.no_grad():
         hidden = tower.forward_hidden(flat)                         # f32 [b*t,257,1024]
     if mode in ("all", "none"):

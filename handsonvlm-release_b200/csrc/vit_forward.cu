@@ -16,6 +16,8 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
                      cudaStream_t s, int reverse);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
+int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv, int n_frames, void* A, const float* cls,
+                     const float* pos, float* x0, cudaStream_t s);
 int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
 
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -98,8 +100,9 @@ extern "C" int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* 
     return launch_gemm(EPI_QKV_HM, A, w_qkv, n_frames * HVLM_VIT_TOKENS, 3072, 1024, ep, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
-                                int n_frames, float* hidden, void* workspace, size_t workspace_bytes, void* stream) {
+static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
+                            const float* u8_mean, const float* u8_std, int n_frames, float* hidden, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     using namespace hvlm;
     if (!weight_blob || !pixels || !hidden || !workspace) return HVLM_ERR_BAD_ARG;
     if (n_frames <= 0 || n_layers_run < 0 || n_layers_run > HVLM_VIT_MAX_LAYERS) return HVLM_ERR_BAD_ARG;
@@ -131,7 +134,11 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
     // embeddings: im2col (+ CLS rows) -> patch GEMM (+ position embedding) -> pre_layrnorm (in place)
     {
         StageTimer st(HVLM_STAGE_IM2COL, s);
-        rc = launch_im2col(pixels, pix_dtype, n_frames, w8 + ws.a_patch, f32(L.cls), f32(L.pos), hidden, s);
+        if (u8_mean)
+            rc = launch_im2col_u8(static_cast<const uint8_t*>(pixels), u8_mean, u8_std, n_frames, w8 + ws.a_patch, f32(L.cls),
+                                  f32(L.pos), hidden, s);
+        else
+            rc = launch_im2col(pixels, pix_dtype, n_frames, w8 + ws.a_patch, f32(L.cls), f32(L.pos), hidden, s);
     }
     if (rc) return rc;
     {
@@ -214,4 +221,20 @@ extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const
         }
     }
     return HVLM_OK;
+}
+
+extern "C" int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
+                                int n_frames, float* hidden, void* workspace, size_t workspace_bytes, void* stream) {
+    return vit_l14_fwd_impl(weight_blob, n_layers_run, pixels, pix_dtype, nullptr, nullptr, n_frames, hidden, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int hvlm_vit_l14_fwd_u8(const void* weight_blob, int n_layers_run, const uint8_t* frames_nhwc,
+                                   const float* mean_host, const float* std_host, int n_frames, float* hidden,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    if (!mean_host || !std_host) return HVLM_ERR_BAD_ARG;
+    for (int c = 0; c < 3; ++c)
+        if (!(std_host[c] > 0.f)) return HVLM_ERR_BAD_ARG;
+    return vit_l14_fwd_impl(weight_blob, n_layers_run, frames_nhwc, HVLM_F32, mean_host, std_host, n_frames, hidden,
+                            workspace, workspace_bytes, stream);
 }

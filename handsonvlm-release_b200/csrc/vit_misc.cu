@@ -127,6 +127,70 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TPix* __restrict__ pi
     }
 }
 
+// uint8 NHWC frames (what a video decoder / PIL hands over) with the CLIPImageProcessor rescale + normalise fused in:
+// value = (u8 / 255 - mean[c]) / std[c].  Same slab staging and output layout as im2col_kernel.
+struct PixelNorm {
+    float scale[3];   // 1 / (255 * std[c])
+    float shift[3];   // -mean[c] / std[c]
+};
+
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ pix, __nv_bfloat16* __restrict__ A,
+                                                        const float* __restrict__ cls, const float* __restrict__ pos0,
+                                                        float* __restrict__ x0, PixelNorm nrm) {
+    __shared__ float slab[3 * 14 * 224];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int gy = blockIdx.x, f = blockIdx.y;
+    // rows gy*14 .. gy*14+13 of frame f are one contiguous run of 14*224*3 bytes in NHWC
+    const uint8_t* base = pix + (static_cast<size_t>(f) * 224 + gy * 14) * 224 * 3;
+    const uint32_t* base4 = reinterpret_cast<const uint32_t*>(base);   // 14*224*3 = 9408 bytes, 4-byte aligned
+    for (int w = threadIdx.x; w < 9408 / 4; w += 256) {
+        const uint32_t v = base4[w];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = 4 * w + k;            // (i*224 + x)*3 + c
+            const int c = idx % 3;
+            const int ix = idx / 3;               // i*224 + x
+            slab[c * 14 * 224 + ix] = static_cast<float>((v >> (8 * k)) & 0xFFu) * nrm.scale[c] + nrm.shift[c];
+        }
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = A + (static_cast<size_t>(f) * 256 + gy * 16) * HVLM_VIT_PATCH_KPAD;
+    for (int idx = threadIdx.x; idx < 16 * (HVLM_VIT_PATCH_KPAD / 2); idx += 256) {
+        const int gx = idx / (HVLM_VIT_PATCH_KPAD / 2);
+        const int col = (idx - gx * (HVLM_VIT_PATCH_KPAD / 2)) * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (col < HVLM_VIT_PATCH_K) {
+            int c = col / 196, r = col - c * 196;
+            int i = r / 14, j = r - i * 14;
+            v0 = slab[c * 14 * 224 + i * 224 + gx * 14 + j];
+            const int col1 = col + 1;
+            c = col1 / 196;
+            r = col1 - c * 196;
+            i = r / 14;
+            j = r - i * 14;
+            v1 = slab[c * 14 * 224 + i * 224 + gx * 14 + j];
+        }
+        *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<size_t>(gx) * HVLM_VIT_PATCH_KPAD + col) =
+            __floats2bfloat162_rn(v0, v1);
+    }
+    if (gy == 0) {
+        float* o = x0 + static_cast<size_t>(f) * HVLM_VIT_TOKENS * 1024;
+        for (int c = threadIdx.x; c < 1024; c += 256) o[c] = cls[c] + pos0[c];
+    }
+}
+
+int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv, int n_frames, void* A, const float* cls,
+                     const float* pos, float* x0, cudaStream_t s) {
+    PixelNorm nrm;
+    for (int c = 0; c < 3; ++c) {
+        nrm.scale[c] = 1.0f / (255.0f * stdv[c]);
+        nrm.shift[c] = -mean[c] / stdv[c];
+    }
+    launch_pdl(im2col_u8_kernel, dim3(16, n_frames), dim3(256), 0, s, frames, static_cast<__nv_bfloat16*>(A), cls, pos, x0, nrm);
+    return check_last("im2col_u8");
+}
+
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s) {
     dim3 grid(16, n_frames);

@@ -174,6 +174,36 @@ def vit_l14_hidden(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run
     return hidden
 
 
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)    # OPENAI_CLIP_MEAN / STD (transformers CLIPImageProcessor defaults)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+@torch.library.custom_op("hvlm::vit_l14_hidden_u8", mutates_args=())
+def vit_l14_hidden_u8(weight_blob: torch.Tensor, frames: torch.Tensor, n_layers_run: int) -> torch.Tensor:
+    """raw uint8 frames [N,224,224,3] (NHWC) -> residual stream f32 [N,257,1024]; rescale + CLIP normalisation fused
+    into the patch extraction."""
+    _need_cuda(weight_blob, frames)
+    ensure_device()
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or tuple(frames.shape[1:]) != (224, 224, 3):
+        raise ValueError(f"expected uint8 frames [N,224,224,3], got {frames.dtype} {tuple(frames.shape)}")
+    frames = frames.contiguous()
+    N = frames.shape[0]
+    lib = L.lib()
+    ws_bytes = lib.hvlm_vit_l14_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+    hidden = torch.empty(N, 257, 1024, dtype=torch.float32, device=frames.device)
+    mean = (C.c_float * 3)(*CLIP_MEAN)
+    std = (C.c_float * 3)(*CLIP_STD)
+    L.check(lib.hvlm_vit_l14_fwd_u8(_p(weight_blob), n_layers_run, _p(frames), mean, std, N, _p(hidden), _p(ws), ws_bytes,
+                                    _stream()), "hvlm_vit_l14_fwd_u8")
+    return hidden
+
+
+@vit_l14_hidden_u8.register_fake
+def _(weight_blob, frames, n_layers_run):
+    return frames.new_empty(frames.shape[0], 257, 1024, dtype=torch.float32)
+
+
 @vit_l14_hidden.register_fake
 def _(weight_blob, pixels, n_layers_run):
     return pixels.new_empty(pixels.shape[0], 257, 1024, dtype=torch.float32)

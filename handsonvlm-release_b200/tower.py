@@ -68,6 +68,9 @@ class CLIPVisionTower(nn.Module):
         """fp32 residual stream [N,257,1024] == HF hidden_states[select_layer] (no copy of the patch rows)."""
         if not self.is_loaded:
             raise RuntimeError("CLIPVisionTower.load_model() has not been called")
+        if images.dtype == torch.uint8:
+            # raw decoded frames [N,224,224,3]: rescale + CLIP normalisation are fused into the patch extraction
+            return ops.vit_l14_hidden_u8(self.weight_blob, images.to(self.device), self.n_layers_needed)
         if images.dtype not in (torch.float32, torch.bfloat16, torch.float16):
             images = images.float()
         return ops.vit_l14_hidden(self.weight_blob, images.to(self.device), self.n_layers_needed)
@@ -81,7 +84,7 @@ class CLIPVisionTower(nn.Module):
                 image_features.append(self.feature_select(hidden, image.dtype))
         else:
             hidden = self.forward_hidden(images)
-            image_features = self.feature_select(hidden, images.dtype)
+            image_features = self.feature_select(hidden, images.dtype if images.is_floating_point() else torch.bfloat16)
         return image_features
 
     # -- properties ----------------------------------------------------------------------------

@@ -139,6 +139,12 @@ HVLM_API size_t hvlm_vit_l14_workspace_bytes(int n_frames);
  */
 HVLM_API int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype, int n_frames,
                      float* hidden, void* workspace, size_t workspace_bytes, void* stream);
+/* Same tower fed with raw uint8 frames [n_frames,224,224,3] (NHWC, as decoded); the CLIPImageProcessor rescale +
+ * normalise ((u8/255 - mean[c]) / std[c], hoi_forecast/dataset/video_utils.py + transformers CLIPImageProcessor) is fused
+ * into the patch extraction, so a clip crosses PCIe as 15 MB instead of 60 MB fp32.  mean/std: 3 floats each, HOST. */
+HVLM_API int hvlm_vit_l14_fwd_u8(const void* weight_blob, int n_layers_run, const uint8_t* frames_nhwc,
+                                 const float* mean_host, const float* std_host, int n_frames, float* hidden,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 /* hidden f32 [n,257,1024] -> feats [n,256,1024] (drop CLS) cast to out_dtype (clip_encoder.py:31-32,49). */
 HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls, void* stream);
 

@@ -532,3 +532,22 @@ def test_visual_token_cache_for_generation(tower23):
     r3 = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px,
                                                    future_hands=fh.to(DEV), future_valid=fv.to(DEV))
     assert host.__dict__["_hvlm_visual_cache"].key is None and r3[3].requires_grad
+
+
+def test_uint8_frames_with_fused_clip_normalisation(tower23):
+    """raw uint8 NHWC frames through the tower == the float path on (u8/255 - mean)/std pixels."""
+    tw, sd = tower23("hf")
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 224, 224, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(ops.CLIP_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.CLIP_STD).view(1, 3, 1, 1)
+    px = (u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    h_u8 = tw.forward_hidden(u8.to(DEV))
+    h_f = tw.forward_hidden(px.to(DEV))
+    assert relmax(h_u8, h_f) <= 3e-3                       # same bf16 operands up to rounding of the normalised pixels
+    ref = restate.vit_hidden(px, sd, 23)
+    assert relmax(h_u8, ref) <= TOL_BF16
+    feats = tw(u8.to(DEV))
+    assert feats.dtype == torch.bfloat16 and feats.shape == (3, 256, 1024)
+    with pytest.raises(ValueError):
+        tw.forward_hidden(torch.zeros(1, 3, 224, 224, dtype=torch.uint8, device=DEV))
