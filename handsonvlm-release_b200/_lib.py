@@ -55,6 +55,7 @@ SIGNATURES = {
     "hvlm_vit_attention": (i32, [p, p, i32, p]),
     "hvlm_pool_out_tokens": (i32, [i32, i32]),
     "hvlm_pool_slowfast_fwd": (i32, [p, i32, i64, p, i32, i32, i32, i32, i32, p]),
+    "hvlm_pool_slowfast_fwd_mapped": (i32, [p, i32, i64, p, p, i32, i32, i32, i32, i32, p]),
     "hvlm_pool_slowfast_bwd": (i32, [p, i32, p, i32, i32, i32, i32, i32, p]),
     "hvlm_splice_count": (i32, [p, i32, i32, p, p]),
     "hvlm_splice_plan": (i32, [p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p]),

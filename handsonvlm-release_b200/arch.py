@@ -74,33 +74,81 @@ class VisualTokenCache:
 
 
 def _cached_video_tokens(host, tower, projector, images, mode):
+    dedup = bool(getattr(host.config, "hvlm_dedup_frames", False))
     if not getattr(host.config, "hvlm_cache_visual_tokens", False):
-        return video_tokens(tower, projector, images, mode)
+        return video_tokens(tower, projector, images, mode, dedup)
     cache = host.__dict__.setdefault("_hvlm_visual_cache", VisualTokenCache())
     extra = (mode, projector.weight.data_ptr(), projector.weight._version, tower.weight_blob.data_ptr())
     tok = cache.get(images, extra)
     if tok is None:
-        tok = video_tokens(tower, projector, images, mode)
+        tok = video_tokens(tower, projector, images, mode, dedup)
         cache.put(images, extra, tok)
     return tok
 
 
-def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str) -> torch.Tensor:
-    """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project)."""
+_HASH_W = {}
+
+
+def distinct_frames(flat: torch.Tensor):
+    """SURVEY 8(f).2 frame de-duplication.  flat [N, ...] -> (rep int64 [U], inverse int32 [N]) with
+    flat[rep[inverse[i]]] == flat[i] bit for bit, or None if every frame is distinct.  A 64-bit weighted checksum groups
+    candidate duplicates, an exact element-wise comparison confirms them (a checksum collision simply disables the
+    de-duplication); costs two streaming passes over the clip and ONE host sync."""
+    N = flat.shape[0]
+    rows = flat.reshape(N, -1)
+    nbytes = rows.shape[1] * rows.element_size()
+    if N < 2 or nbytes % 4 != 0:
+        return None
+    words = rows.view(torch.int32)
+    key = (words.shape[1], flat.device)
+    w = _HASH_W.get(key)
+    if w is None:
+        g = torch.Generator(device="cpu").manual_seed(0x5EED)
+        w = torch.randint(-(2 ** 31), 2 ** 31 - 1, (words.shape[1],), generator=g, dtype=torch.int64).to(flat.device) | 1
+        _HASH_W[key] = w
+    h = (words.to(torch.int64) * w).sum(dim=1)                         # wrap-around int64 arithmetic
+    uniq, inverse = torch.unique(h, return_inverse=True)
+    U = uniq.numel()                                                  # host sync (size of a data-dependent result)
+    if U == N:
+        return None
+    rep = torch.full((U,), N, dtype=torch.int64, device=flat.device).scatter_reduce_(
+        0, inverse, torch.arange(N, device=flat.device), reduce="amin")
+    exact = bool((rows == rows[rep[inverse]]).all())                  # confirm: no checksum collision
+    if not exact:
+        return None
+    return rep, inverse.to(torch.int32)
+
+
+def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str, dedup: bool = False) -> torch.Tensor:
+    """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project).  With ``dedup`` the tower only
+    encodes the distinct frames of the batch and the pooling reads them through a frame map."""
     assert images.ndim == 5, "multiple videos per sample not supported yet"
     b, t = images.shape[:2]
     flat = images.reshape(b * t, *images.shape[2:])      # [b*t,3,224,224] float, or raw uint8 [b*t,224,224,3]
+    fmap = None
+    if dedup:
+        d = distinct_frames(flat)
+        if d is not None:
+            rep, fmap = d
+            flat = flat.index_select(0, rep)
     with torch.no_grad():
-        hidden = tower.forward_hidden(flat)                         # f32 [b*t,257,1024]
+        hidden = tower.forward_hidden(flat)                         # f32 [n_distinct,257,1024]
     if mode in ("all", "none"):
-        feats = tower.feature_select(hidden, torch.bfloat16)        # [b*t,256(+1),1024]
+        feats = tower.feature_select(hidden, torch.bfloat16)        # [n_distinct,256(+1),1024]
+        if fmap is not None:
+            feats = feats.index_select(0, fmap.to(torch.int64))
         tok = _project(projector, feats.reshape(-1, feats.shape[-1]))
         return tok.reshape(b, t * feats.shape[1], -1)
     if mode not in _POOLED:
         raise ValueError(f"unknown video arch {mode}")
     if tower.select_feature != "patch":
         raise AssertionError(f"tokens.shape = {(b * t, 257, projector.out_features)}")   # reference asserts 256 tokens
-    pooled = ops.pool_slowfast(hidden, b, t, 257, 1, L.POOL_MODES[mode], True)   # bf16 [b,Nv,1024]
+    if fmap is not None and mode in ("temporal_spatial_pool", "spatial_pool", "temporal"):
+        pooled = ops.pool_slowfast_mapped(hidden, fmap, b, t, 257, 1, L.POOL_MODES[mode], True)
+    else:
+        if fmap is not None:
+            hidden = hidden.index_select(0, fmap.to(torch.int64))
+        pooled = ops.pool_slowfast(hidden, b, t, 257, 1, L.POOL_MODES[mode], True)   # bf16 [b,Nv,1024]
     tok = _project(projector, pooled.reshape(-1, 1024))
     return tok.reshape(b, pooled.shape[1], -1)
 

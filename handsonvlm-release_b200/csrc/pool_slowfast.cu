@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) pool_slowfast_fwd_kernel(const TIn* __res
                                                                 TOut* __restrict__ out, int t, int C, int n_out,
                                                                 int fast_row0 /* -1: no fast rows */,
                                                                 int slow_row0 /* -1: no slow rows */, SelFrames sf,
-                                                                int frames_from_sel) {
+                                                                int frames_from_sel,
+                                                                const int32_t* __restrict__ frame_map) {
     constexpr int V = Vec16<TIn>::N;         // channels per lane
     constexpr int SLAB = 16 * V;             // channels per CTA
     __shared__ float red[8][16][V];
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(256) pool_slowfast_fwd_kernel(const TIn* __res
         }
     }
 
-    const TIn* src = tok + (static_cast<int64_t>(b) * t + f) * frame_stride * C + c0 + cl;
+    // optional indirection (frame de-duplication): logical frame (b,f) lives at row block frame_map[b*t+f]
+    const int64_t fsrc = frame_map ? static_cast<int64_t>(frame_map[b * t + f]) : static_cast<int64_t>(b) * t + f;
+    const TIn* src = tok + fsrc * frame_stride * C + c0 + cl;
     float facc[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) facc[i] = 0.f;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) pool_slowfast_bwd_kernel(const TIn* __res
 
 template <typename TIn, typename TOut>
 static int pool_fwd_typed(const void* tok, int64_t frame_stride, void* out, int B, int t, int C, int mode,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int32_t* frame_map = nullptr) {
     constexpr int V = Vec16<TIn>::N;
     if (C % V != 0) return HVLM_ERR_BAD_SHAPE;
     const int n_out = hvlm_pool_out_tokens(t, mode);
@@ -227,19 +230,20 @@ static int pool_fwd_typed(const void* tok, int64_t frame_stride, void* out, int 
     TOut* o = static_cast<TOut*>(out);
     switch (mode) {
         case HVLM_POOL_TEMPORAL_SPATIAL_POOL:
-            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, t, sf, 0);
+            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, t, sf, 0, frame_map);
             break;
         case HVLM_POOL_SPATIAL_POOL:
-            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, 4, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, -1, 0, sf, 1);
+            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, 4, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, -1, 0, sf, 1, frame_map);
             break;
         case HVLM_POOL_TEMPORAL:
-            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, -1, sf, 0);
+            pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, -1, sf, 0, frame_map);
             break;
         case HVLM_POOL_SPATIAL:
         case HVLM_POOL_TEMPORAL_SPATIAL: {
+            if (frame_map) return HVLM_ERR_UNSUPPORTED;
             int row0 = 0;
             if (mode == HVLM_POOL_TEMPORAL_SPATIAL) {
-                pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, -1, sf, 0);
+                pool_slowfast_fwd_kernel<TIn, TOut><<<dim3(slabs, t, B), 256, 0, s>>>(in, frame_stride, o, t, C, n_out, 0, -1, sf, 0, frame_map);
                 row0 = t;
             }
             const int gx = (C / V + 127) / 128;
@@ -309,5 +313,20 @@ extern "C" int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dt
     if (dout_dtype == HVLM_BF16 && dtok_dtype == HVLM_BF16) return pool_bwd_typed<__nv_bfloat16, __nv_bfloat16>(dout, dtok, B, t, C, mode, s);
     if (dout_dtype == HVLM_F32 && dtok_dtype == HVLM_BF16) return pool_bwd_typed<float, __nv_bfloat16>(dout, dtok, B, t, C, mode, s);
     if (dout_dtype == HVLM_BF16 && dtok_dtype == HVLM_F32) return pool_bwd_typed<__nv_bfloat16, float>(dout, dtok, B, t, C, mode, s);
+    return HVLM_ERR_BAD_DTYPE;
+}
+
+extern "C" int hvlm_pool_slowfast_fwd_mapped(const void* tok, int in_dtype, int64_t frame_stride, const int32_t* frame_map,
+                                             void* out, int out_dtype, int B, int t, int C, int mode, void* stream) {
+    using namespace hvlm;
+    if (!tok || !out || !frame_map || B <= 0 || t <= 0 || C <= 0) return HVLM_ERR_BAD_ARG;
+    if (frame_stride < 256) return HVLM_ERR_BAD_SHAPE;
+    if (!aligned16(tok) || !aligned16(out)) return HVLM_ERR_ALIGN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_POOL, s);
+    if (in_dtype == HVLM_F32 && out_dtype == HVLM_F32) return pool_fwd_typed<float, float>(tok, frame_stride, out, B, t, C, mode, s, frame_map);
+    if (in_dtype == HVLM_F32 && out_dtype == HVLM_BF16) return pool_fwd_typed<float, __nv_bfloat16>(tok, frame_stride, out, B, t, C, mode, s, frame_map);
+    if (in_dtype == HVLM_BF16 && out_dtype == HVLM_BF16) return pool_fwd_typed<__nv_bfloat16, __nv_bfloat16>(tok, frame_stride, out, B, t, C, mode, s, frame_map);
+    if (in_dtype == HVLM_BF16 && out_dtype == HVLM_F32) return pool_fwd_typed<__nv_bfloat16, float>(tok, frame_stride, out, B, t, C, mode, s, frame_map);
     return HVLM_ERR_BAD_DTYPE;
 }

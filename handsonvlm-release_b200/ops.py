@@ -333,6 +333,24 @@ def _pool_backward(ctx, dout):
 pool_slowfast.register_autograd(_pool_backward, setup_context=_pool_setup)
 
 
+def pool_slowfast_mapped(tok: torch.Tensor, frame_map: torch.Tensor, B: int, t: int, frame_stride: int, row_offset: int,
+                         mode: int, out_bf16: bool) -> torch.Tensor:
+    """pool_slowfast with a frame indirection (frame de-duplication): tok [n_unique, frame_stride, C], frame_map int32
+    [B*t] -> [B, n_out, C].  Forward only (the tower output never requires grad)."""
+    _need_cuda(tok, frame_map)
+    ensure_device()
+    assert tok.is_contiguous() and tok.dim() == 3 and tok.shape[1] == frame_stride and row_offset + 256 <= frame_stride
+    assert frame_map.dtype == torch.int32 and frame_map.numel() == B * t and frame_map.is_contiguous()
+    Cc = tok.shape[2]
+    lib = L.lib()
+    n_out = lib.hvlm_pool_out_tokens(t, mode)
+    out = torch.empty(B, n_out, Cc, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=tok.device)
+    base = C.c_void_p(tok.data_ptr() + row_offset * Cc * tok.element_size())
+    L.check(lib.hvlm_pool_slowfast_fwd_mapped(base, _dt(tok), frame_stride, _p(frame_map), _p(out), _DT[out.dtype], B, t, Cc,
+                                              mode, _stream()), "hvlm_pool_slowfast_fwd_mapped")
+    return out
+
+
 def pool_tokens(tokens: torch.Tensor, mode: str, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """tokens [b,t,256,C] -> [b,n_out,C]  (compress_tokens / videos_to_tokens pooling)."""
     b, t, s, c = tokens.shape

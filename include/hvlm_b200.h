@@ -171,6 +171,11 @@ HVLM_API int hvlm_vit_attention(const void* qkv_hm, void* out, int n_frames, voi
 HVLM_API int hvlm_pool_out_tokens(int t, int mode);
 HVLM_API int hvlm_pool_slowfast_fwd(const void* tok, int in_dtype, int64_t frame_stride, void* out, int out_dtype, int B,
                            int t, int C, int mode, void* stream);
+/* Same, with a frame indirection: logical frame (b,f) is read from row block frame_map[b*t+f] of `tok` (frame
+ * de-duplication: EPIC clips are 10 distinct frames tiled x10, handsonvlm/dataset/epic_dataset.py:90-95; single images are
+ * tiled x100, hybrid_dataset.py:141-142 -- the tower then only encodes the distinct frames).  Modes 0,1,2 only. */
+HVLM_API int hvlm_pool_slowfast_fwd_mapped(const void* tok, int in_dtype, int64_t frame_stride, const int32_t* frame_map,
+                                           void* out, int out_dtype, int B, int t, int C, int mode, void* stream);
 /* d_tok [B,t,256,C] (dense) = autograd of the above wrt tok; dout [B,n_out,C]. */
 HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok, int dtok_dtype, int B, int t, int C,
                            int mode, void* stream);

@@ -551,3 +551,31 @@ def test_uint8_frames_with_fused_clip_normalisation(tower23):
     assert feats.dtype == torch.bfloat16 and feats.shape == (3, 256, 1024)
     with pytest.raises(ValueError):
         tw.forward_hidden(torch.zeros(1, 3, 224, 224, dtype=torch.uint8, device=DEV))
+
+
+def test_frame_dedup_tiled_clip(tower23):
+    """an EPIC-style clip (10 distinct frames tiled x10) is encoded once per distinct frame; tokens are
+    bit-identical to the undeduplicated path, and the tower launches ~10x fewer frames."""
+    tw, sd = tower23("hf")
+    D = 256
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    proj = proj.to(DEV)
+    base = synth.pixels((4, 3, 224, 224), seed=21).to(torch.bfloat16)
+    clip = base.repeat_interleave(5, dim=0).unsqueeze(0).to(DEV)          # [1,20,3,224,224], 4 distinct frames
+    d = arch.distinct_frames(clip[0])
+    assert d is not None and d[0].numel() == 4
+    assert d[0][d[1].long()].tolist() == [5 * (i // 5) for i in range(20)]      # every frame -> first occurrence
+    assert arch.distinct_frames(synth.pixels((5, 3, 224, 224), seed=22).to(DEV)) is None
+    with torch.no_grad():
+        for mode in ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "none"):
+            ref = arch.video_tokens(tw, proj, clip, mode, dedup=False)
+            out = arch.video_tokens(tw, proj, clip, mode, dedup=True)
+            assert torch.equal(out, ref), mode
+    # mixed batch: two clips sharing frames across the batch dimension
+    clip2 = torch.cat([clip, clip.flip(1)], 0)
+    with torch.no_grad():
+        assert torch.equal(arch.video_tokens(tw, proj, clip2, "temporal_spatial_pool", True),
+                           arch.video_tokens(tw, proj, clip2, "temporal_spatial_pool", False))
