@@ -23,13 +23,16 @@ namespace gemm2 {
 constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int BN = 256;          // columns per pair (each CTA loads 128 of them)
 constexpr int BK = 64;
-constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
-constexpr int kStages = 6;
+constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue (+ warps 6..9: 2nd epilogue group)
+template <int G>                 // G = number of 4-warp epilogue groups (each owns half of the tile's columns when G == 2)
+struct Cfg2 {
+    static constexpr int kStages = (G == 2) ? 5 : 6;
+    static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * 2 * (BM * 128) + 1024 + 256;
+};
 constexpr int kABytes = BM * BK * 2;            // 16 KB
 constexpr int kBBytes = (BN / 2) * BK * 2;      // 16 KB (this CTA's half of B)
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kStoreBuf = BM * 128;
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kStoreBuf + 1024 + 256;
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -136,18 +139,20 @@ __device__ __forceinline__ void ln_rows(const float* __restrict__ x, const float
     }
 }
 
-template <int EPI, bool LN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + (LN ? 128 : 0), 1)
+template <int EPI, bool LN, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2) ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiArgs ep) {
     static_assert(epi_is_staged<EPI>(), "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
+    static_assert(!(LN && G == 2), "the fused-LayerNorm warps and the second epilogue group use the same warp slots");
+    constexpr int kStages = Cfg2<G>::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kABytes;
     uint8_t* smem_c = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * kStoreBuf);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + G * 2 * kStoreBuf);
     uint64_t* full_bar = bars;                       // [kStages]  TMA (both CTAs) -> MMA        (leader's copy is used)
     uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA                    (multicast to both)
     uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue               (multicast to both)
@@ -174,7 +179,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 256);   // 128 epilogue threads in each CTA of the pair
+            mbar_init(&tempty_bar[i], 256 * G);   // 128*G epilogue threads in each CTA of the pair
         }
         fence_mbar_init();
     }
@@ -249,17 +254,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 }
             }
         }
-    } else if (warp < 6) {
-        // ===================== epilogue warps (2..5), both CTAs: own 128 x 256 half =====================
+    } else if (warp < 2 + 4 * G) {
+        // ===================== epilogue warps, both CTAs: own 128 x 256 half =====================
+        // G == 2: warps 2..5 take the tile's left 128 columns, warps 6..9 the right 128 (own staging buffers, own
+        // store thread, own named barriers) -- doubles the epilogue throughput for the short-K / fp32-output GEMMs
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr bool kF32 = epi_out_f32<EPI>();
         constexpr int kUnitCols = kF32 ? 32 : 64;
-        constexpr int kUnits = BN / kUnitCols;
+        constexpr int kUnits = BN / kUnitCols / G;          // units per group
+        const int u0 = grp * kUnits;                        // first unit of this group
         const int row = q * 32 + lane;
         const int sw = row & 7;
-        const bool store_warp = (warp == 2);
+        const bool store_warp = (((warp - 2) & 3) == 0);
+        uint8_t* smem_cg = smem_c + grp * 2 * kStoreBuf;
+        const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
         uint32_t ucount = 0;
         int pending_rb = -1;
         for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
@@ -271,14 +282,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-            for (int u = 0; u < kUnits; ++u, ++ucount) {
-                uint8_t* buf = smem_c + (ucount & 1u) * kStoreBuf;
+            for (int uu = 0; uu < kUnits; ++uu, ++ucount) {
+                const int u = u0 + uu;
+                uint8_t* buf = smem_cg + (ucount & 1u) * kStoreBuf;
                 uint8_t* brow = buf + row * 128;
                 if (store_warp) {
                     if (elect_one()) bulk_wait_read<1>();
                     __syncwarp();
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(bar_a, 128);
                 const int n0 = n_blk * BN + u * kUnitCols;
 #pragma unroll
                 for (int h = 0; h < kUnitCols / 32; ++h) {
@@ -304,14 +316,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         }
                     }
                 }
-                if (u == kUnits - 1) {
-                    // last TMEM read of this accumulator: release it to the (leader's) MMA warp
+                if (uu == kUnits - 1) {
+                    // last TMEM read of this accumulator by this group: release it to the (leader's) MMA warp
                     tc_fence_before();
                     if (rank == 0) mbar_arrive(&tempty_bar[acc]);
                     else mbar_arrive_cluster(&tempty_bar[acc], 0);
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(2, 128);
+                named_bar_sync(bar_b, 128);
                 if (store_warp) {
                     if (elect_one()) {
                         if constexpr (EPI == EPI_RESID_F32) {
@@ -380,7 +392,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         ln_rows<2>(hidden + static_cast<size_t>(row) * 1024, ep.ln_gamma, ep.ln_beta,
                                    y + static_cast<size_t>(row) * 1024, nrows, lane);
                 }
-                named_bar_sync(3, 128);
+                named_bar_sync(5, 128);
                 if (lw == 0 && lane == 0) ep.ln_count[rb] = 0;     // leave the counters clean for the next launch
             }
         }
@@ -392,7 +404,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (warp == 1) tmem_dealloc_2sm(tmem_base);
 }
 
-template <int EPI, bool LN = false>
+template <int EPI, bool LN = false, int G = 1>
 static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     CUtensorMap ta, tb, tc;
     {
@@ -427,7 +439,8 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         }
         if (rc) return rc;
     }
-    auto kern = gemm2_tcgen05_kernel<EPI, LN>;
+    auto kern = gemm2_tcgen05_kernel<EPI, LN, G>;
+    constexpr int kSmemBytes = Cfg2<G>::kSmemBytes;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -439,7 +452,7 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + (LN ? 128 : 0)), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
+    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + ((LN || G == 2) ? 128 : 0)), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
     }
@@ -452,6 +465,16 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
 int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     using namespace gemm2;
     if ((N % BN) != 0) return HVLM_ERR_UNSUPPORTED;
+    // The quick-GELU epilogue is math-bound on 4 warps (measured 156.7 us vs 146.0 us for the plain bf16 store on
+    // 25700x4096x1024); a second 4-warp group brings it to 149.7 us.  The fp32 store / reduce-add epilogues are bound by
+    // the store traffic instead and measured no gain, so they keep 4 warps and the 6-stage pipeline.
+    // HVLM_GEMM_EPI_GROUPS=1 forces the single group for A/B runs.
+    static const bool two_groups = []() {
+        const char* e = getenv("HVLM_GEMM_EPI_GROUPS");
+        return !(e && e[0] == '1');
+    }();
+    if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
+        return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
     switch (epi) {
         case EPI_BIAS_BF16: return launch_two<EPI_BIAS_BF16>(A, B, M, N, K, ep, s);
         case EPI_BIAS_F32: return launch_two<EPI_BIAS_F32>(A, B, M, N, K, ep, s);
