@@ -15,7 +15,7 @@ def build(verbose: bool = False) -> str:
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `build()` works before torch is paged in
-    if name in ("ops", "tower", "arch", "weights", "dist"):
+    if name in ("ops", "tower", "arch", "weights", "dist", "traj_decoder"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("CLIPVisionTower",):
@@ -25,4 +25,7 @@ def __getattr__(name):
                 "gather_hand_traj_states"):
         from . import arch
         return getattr(arch, name)
+    if name == "CVAETrajDecoder":
+        from .traj_decoder import CVAETrajDecoder
+        return CVAETrajDecoder
     raise AttributeError(name)

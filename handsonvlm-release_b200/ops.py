@@ -535,6 +535,52 @@ def _gather_backward(ctx, dout, dvalid, drows, dcounts):
 hand_gather.register_autograd(_gather_backward, setup_context=_gather_setup)
 
 
+_traj_ws: dict = {}
+
+
+def _traj_workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch for hvlm_traj_decode, one per (device, stream); the kernel leaves it zeroed."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _traj_ws.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+        _traj_ws[key] = ws
+    return ws
+
+
+def traj_decode(cond: torch.Tensor, z: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+                b2: torch.Tensor, interleaved: bool = False) -> torch.Tensor:
+    """CVAE trajectory decoder, generation side (TrajCVAE.inference, hoi_forecast/architecture/traj_decoder.py:75-91):
+    ``ELU(cat(z, cond) W1^T + b1) W2^T + b2`` in one launch -> [R, 2] fp32.
+
+    cond [R, Dc] (``interleaved=False``) or the raw last hidden rows [R/2, 2*Dc] (``interleaved=True``: the even/odd
+    de-interleave of handsonvlm.py:613-616 happens inside the kernel).  z [R, L] is the already scaled noise."""
+    _need_cuda(cond)
+    ensure_device()
+    if cond.dim() != 2 or z.dim() != 2:
+        raise AssertionError((cond.shape, z.shape))
+    if cond.stride(1) != 1:
+        cond = cond.contiguous()
+    R, Lz = z.shape
+    Dc = cond.shape[1] // 2 if interleaved else cond.shape[1]
+    H = w1.shape[0]
+    if interleaved:
+        assert cond.shape[0] * 2 == R and cond.shape[1] == 2 * Dc, (cond.shape, z.shape)
+    else:
+        assert cond.shape[0] == R, (cond.shape, z.shape)
+    assert w1.shape == (H, Lz + Dc) and b1.shape == (H,) and w2.shape == (2, H) and b2.shape == (2,), \
+        (w1.shape, b1.shape, w2.shape, b2.shape)
+    dt = cond.dtype
+    z, w1, b1, w2, b2 = (t.to(dt).contiguous() for t in (z, w1, b1, w2, b2))
+    out = torch.empty(R, 2, dtype=torch.float32, device=cond.device)
+    need = int(L.lib().hvlm_traj_decode_workspace_bytes(R, H))
+    ws = _traj_workspace(cond.device, need)
+    L.check(L.lib().hvlm_traj_decode(_p(cond), cond.stride(0), int(interleaved), _p(z), _p(w1), _p(b1), _p(w2), _p(b2),
+                                     _dt(cond), R, Dc, Lz, H, _p(out), _p(ws), ws.numel(), _stream()),
+            "hvlm_traj_decode")
+    return out
+
+
 def hand_gather_step(hidden_last: torch.Tensor) -> torch.Tensor:
     """Generation-time gather (handsonvlm.py:613-616): [B,D] -> [B,2,1,D/2]."""
     _need_cuda(hidden_last)

@@ -240,6 +240,25 @@ HVLM_API int hvlm_hand_gather_bwd(const void* dout, int dtype, const int32_t* ro
 HVLM_API int hvlm_hand_gather_step(const void* hidden_last, int dtype, int B, int D, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * trajectory head after the gather, generation side -- replaces, in one launch, the <hand_traj> branch of the sampling
+ * loop  handsonvlm/.../handsonvlm.py:609-622  ->  TrajDecoder.inference  handsonvlm/.../traj_decoder.py:39-47
+ *   ->  TrajCVAE.inference  hoi_forecast/architecture/traj_decoder.py:75-91  ->  VAE.inference  decoder_modules.py:56-60:
+ *   out[r,:] = W2 . ELU(W1 . cat(z[r], cond[r]) + b1) + b2        W1 [H, L+Dc], W2 [2, H]   (dec_MLP.0 / dec_MLP.2)
+ * cond source: interleaved = 0: cond [R, Dc] rows with stride ld_cond (elements) -- the reshaped pred_hand_embeddings;
+ *              interleaved = 1: cond = last hidden rows [R/2, >= 2*Dc], row r = (b, hand) reads hidden[b, 2j + hand]
+ *              (the gather of handsonvlm.py:613-616 fused in; R must be even).
+ * z [R, L] is the caller-drawn, already scaled noise (the reference draws z_scale * randn itself, traj_decoder.py:87).
+ * All tensors share `dtype`; out [R, 2] is fp32.  workspace: >= hvlm_traj_decode_workspace_bytes(R, H) bytes whose first
+ * 4096 bytes (arrival counters) are zeroed ONCE by the caller before the first use -- every call leaves them zeroed,
+ * whatever its R and H, so one buffer sized for the largest call can be reused; one workspace per stream.
+ * Accumulation order is fixed: results are bit-reproducible run to run.
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API size_t hvlm_traj_decode_workspace_bytes(int R, int H);
+HVLM_API int hvlm_traj_decode(const void* cond, int64_t ld_cond, int interleaved, const void* z, const void* W1, const void* b1,
+                     const void* W2, const void* b2, int dtype, int R, int Dc, int L, int H, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * helpers for the training-shaped variant
  * ---------------------------------------------------------------------------------------------- */
 /* out bf16 [C, R_pad] = in[R, C]^T (zero padded to R_pad, a multiple of 8): makes dY / X K-major for wgrad. */

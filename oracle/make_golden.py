@@ -276,6 +276,33 @@ def golden_gather(ns):
     save("gather_pos0", out=out, future_valid=fv2, labels=labels)
 
 
+def golden_traj(ns):
+    """The reference's CVAETrajDecoder.inference (generation side of the trajectory head), run as
+    is; the noise it draws internally is reproduced by reseeding torch's global generator and stored with the output."""
+    import importlib
+    mod = importlib.import_module("handsonvlm.model.language_model.traj_decoder")
+    Dc = 32
+    dec = mod.CVAETrajDecoder(token_dim=Dc)
+    sd = synth.traj_cvae_state(Dc, seed=3)
+    dec.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        # general inference: [B,2,T_pred,Dc]
+        emb = synth.gen("traj_emb", (3, 2, 4, Dc), 1.0, seed=51)
+        torch.manual_seed(1234)
+        out = dec.inference(pred_hand_embeddings=emb)
+        torch.manual_seed(1234)
+        z = dec.hand_traj_decoder.z_scale * torch.randn([3 * 2 * 4, 256])
+        save("traj_infer", out=out, z=z)
+        # the generation step exactly as handsonvlm.py:613-620 does it (batch 1)
+        hidden_last = synth.gen("traj_hidden_last", (1, 2 * Dc), 1.0, seed=52)
+        e = hidden_last.reshape(1, Dc, 2).permute(0, 2, 1).unsqueeze(2)
+        torch.manual_seed(77)
+        out = dec.inference(pred_hand_embeddings=e).squeeze(2)
+        torch.manual_seed(77)
+        z = dec.hand_traj_decoder.z_scale * torch.randn([2, 256])
+        save("traj_step", out=out, z=z)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -284,6 +311,7 @@ def main():
         raise ns.handsonvlm_error
     golden_pool(ns)
     golden_gather(ns)
+    golden_traj(ns)
     golden_lita(ns)
     golden_splice(ns)
     golden_vit_full(ns)

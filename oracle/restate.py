@@ -366,6 +366,36 @@ def gather_hand_traj_step(hidden_last: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# trajectory head after the gather, generation side
+# ----------------------------------------------------------------------------------------
+
+def traj_cvae_inference(cond: torch.Tensor, z: torch.Tensor, sd: dict) -> torch.Tensor:
+    """``TrajCVAE.inference`` with ``condition_contact=False`` (hoi_forecast/architecture/traj_decoder.py:75-91) ->
+    ``VAE.inference`` (decoder_modules.py:56-60): ``dec_MLP(cat(z, cond))`` with
+    ``dec_MLP = Linear(latent + token_dim, hidden), ELU, Linear(hidden, 2)`` (decoder_modules.py:26-29).
+    cond [R, token_dim], z [R, latent] -- the ALREADY SCALED noise (the reference draws
+    ``z_scale * torch.randn([R, latent])`` itself, traj_decoder.py:87) -> [R, 2].  fp32 throughout."""
+    pre = "hand_traj_decoder.cvae.dec_MLP."
+    x = torch.cat([z.float(), cond.float()], dim=-1)
+    h = x @ sd[pre + "0.weight"].float().t() + sd[pre + "0.bias"].float()
+    h = torch.where(h > 0, h, torch.expm1(h))                                   # nn.ELU(alpha=1)
+    return h @ sd[pre + "2.weight"].float().t() + sd[pre + "2.bias"].float()
+
+
+def traj_decoder_inference(pred_hand_embeddings: torch.Tensor, z: torch.Tensor, sd: dict) -> torch.Tensor:
+    """``TrajDecoder.inference`` (handsonvlm/model/language_model/traj_decoder.py:39-47):
+    [B,2,T_pred,token_dim] -> rows (b,hand,k) -> [B,2,T_pred,2]."""
+    B, _, T_pred, Dc = pred_hand_embeddings.shape
+    return traj_cvae_inference(pred_hand_embeddings.reshape(-1, Dc), z, sd).reshape(B, 2, T_pred, 2)
+
+
+def traj_decode_step(hidden_last: torch.Tensor, z: torch.Tensor, sd: dict) -> torch.Tensor:
+    """The generation loop's ``<hand_traj>`` branch in one call (handsonvlm.py:609-622): gather the last hidden
+    row (even/odd de-interleave) and decode it -> [B,2,2] (the ``.squeeze(2)`` of handsonvlm.py:620)."""
+    return traj_decoder_inference(gather_hand_traj_step(hidden_last), z, sd).squeeze(2)
+
+
+# ----------------------------------------------------------------------------------------
 # whole path (VisualToTokenHelper.pipeline, visual_to_tokens.py:23-37)
 # ----------------------------------------------------------------------------------------
 

@@ -122,6 +122,20 @@ def projector_state(D: int, E: int = 1024, seed: int = 1) -> dict:
             "mm_projector.bias": gen("proj.b", (D,), bound * 0.577, seed)}
 
 
+def traj_cvae_state(token_dim: int, hidden: int = 512, latent: int = 256, in_dim: int = 2, seed: int = 1) -> dict:
+    """State dict of ``CVAETrajDecoder(token_dim)`` (handsonvlm/model/language_model/traj_decoder.py:60-70 ->
+    TrajCVAE -> VAE, hoi_forecast/architecture/decoder_modules.py:5-30), keys as the reference names them,
+    nn.Linear-like scale.  ``token_dim`` here is the per-hand width D/2."""
+    pre = "hand_traj_decoder.cvae."
+    shapes = {"enc_MLP.0": (hidden, in_dim + token_dim), "linear_means": (latent, hidden),
+              "linear_log_var": (latent, hidden), "dec_MLP.0": (hidden, latent + token_dim), "dec_MLP.2": (in_dim, hidden)}
+    sd = {}
+    for k, (o, i) in shapes.items():
+        sd[pre + k + ".weight"] = gen("traj." + k + ".w", (o, i), 0.577 * i ** -0.5, seed)
+        sd[pre + k + ".bias"] = gen("traj." + k + ".b", (o,), 0.577 * i ** -0.5, seed)
+    return sd
+
+
 def embed_table(D: int, vocab: int = VOCAB, seed: int = 1) -> torch.Tensor:
     """``embed_tokens = nn.Embedding(vocab, D)`` -- N(0,1) like nn.Embedding's default."""
     return gen("embed_tokens", (vocab, D), 1.0, seed)

@@ -174,6 +174,77 @@ def test_gather_backward_and_step():
     assert torch.equal(ops.hand_gather_step(last.to(DEV)).cpu(), restate.gather_hand_traj_step(last))
 
 
+# ------------------------------------------------------------------ trajectory head (8f item 4)
+def _traj_module(Dc, seed, dtype):
+    from hvlm_b200.traj_decoder import CVAETrajDecoder
+    sd = synth.traj_cvae_state(Dc, seed=seed)
+    dec = CVAETrajDecoder(token_dim=Dc)
+    dec.load_state_dict(sd, strict=True)            # the reference's own key names
+    return dec.to(DEV).to(dtype), sd
+
+
+def test_traj_head_golden():
+    """fp32 weights, the reference's noise from the fixture: the fused kernel vs the reference's own output."""
+    dec, sd = _traj_module(32, 3, torch.float32)
+    g = np.load("tests/golden/traj_infer.npz")
+    emb = synth.gen("traj_emb", (3, 2, 4, 32), 1.0, seed=51).to(DEV)
+    out = dec.inference(pred_hand_embeddings=emb, z=T(g["z"]).to(DEV))
+    assert out.shape == (3, 2, 4, 2)
+    assert relmax(out, T(g["out"])) <= 3e-5, relmax(out, T(g["out"]))
+    g = np.load("tests/golden/traj_step.npz")
+    hl = synth.gen("traj_hidden_last", (1, 64), 1.0, seed=52).to(DEV)
+    out = dec.inference_step(hl, z=T(g["z"]).to(DEV))
+    assert out.shape == (1, 2, 2)
+    assert relmax(out, T(g["out"])) <= 3e-5, relmax(out, T(g["out"]))
+
+
+@pytest.mark.parametrize("D,B", [(4096, 1), (5120, 1), (4096, 3)])
+def test_traj_head_step_full_size(D, B):
+    """7B / 13B widths in bf16: fused gather+decode vs the fp32 oracle on the same (bf16-rounded) operands; internally
+    drawn noise must reproduce torch.randn under the same seed; bit-reproducible run to run."""
+    Dc = D // 2
+    dec, sd = _traj_module(Dc, 5, torch.bfloat16)
+    sd16 = {k: v.to(torch.bfloat16).float() for k, v in sd.items()}
+    hl = synth.gen("traj_hl", (B, D), 1.0, seed=9).to(torch.bfloat16)
+    torch.manual_seed(99)
+    out = dec.inference_step(hl.to(DEV))
+    torch.manual_seed(99)
+    z = (2.0 * torch.randn([2 * B, 256], device=DEV)).to(torch.bfloat16)
+    ref = restate.traj_decode_step(hl.float(), z.float().cpu(), sd16)
+    assert out.dtype == torch.bfloat16 and out.shape == (B, 2, 2)
+    assert relmax(out, ref) <= TOL_BF16
+    # fp32 result of the kernel itself (before the cast back to bf16) is tight
+    d = dec.hand_traj_decoder.cvae.dec_MLP
+    raw = ops.traj_decode(hl.to(DEV), z, d[0].weight, d[0].bias, d[2].weight, d[2].bias, interleaved=True)
+    assert relmax(raw.reshape(B, 2, 2), ref) <= 1e-4
+    raw2 = ops.traj_decode(hl.to(DEV), z, d[0].weight, d[0].bias, d[2].weight, d[2].bias, interleaved=True)
+    assert torch.equal(raw, raw2)
+    # the two-call form (gather, then decode) gives the same bits
+    e = ops.hand_gather_step(hl.to(DEV))
+    raw3 = ops.traj_decode(e.reshape(-1, Dc), z, d[0].weight, d[0].bias, d[2].weight, d[2].bias)
+    assert torch.equal(raw, raw3)
+
+
+def test_traj_head_many_rows_and_errors():
+    dec, sd = _traj_module(64, 6, torch.float32)
+    emb = synth.gen("traj_emb2", (5, 2, 3, 64), 1.0, seed=10)      # R = 30: several row chunks, ragged tail
+    z = synth.gen("traj_z2", (30, 256), 2.0, seed=10)
+    out = dec.inference(pred_hand_embeddings=emb.to(DEV), z=z.to(DEV))
+    assert relmax(out, restate.traj_decoder_inference(emb, z, sd)) <= 1e-5
+    # more rows than one launch covers (4096): the C entry splits the rows over launches
+    emb = synth.gen("traj_emb3", (2051, 2, 1, 64), 1.0, seed=11)
+    z = synth.gen("traj_z3", (4102, 256), 2.0, seed=11)
+    out = dec.inference(pred_hand_embeddings=emb.to(DEV), z=z.to(DEV))
+    assert relmax(out, restate.traj_decoder_inference(emb, z, sd)) <= 1e-5
+    emb = synth.gen("traj_emb", (3, 2, 4, 64), 1.0, seed=51)
+    with pytest.raises(AssertionError):
+        dec.inference(pred_hand_embeddings=emb[..., :32].to(DEV))
+    with pytest.raises(RuntimeError):
+        dec.inference(pred_hand_embeddings=emb)                     # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        dec(pred_hand_embeddings=emb.to(DEV))
+
+
 # ------------------------------------------------------------------ splice
 class _Inner(torch.nn.Module):
     def __init__(self, tower, proj, emb):

@@ -48,6 +48,26 @@ def test_pool_backward_matches_reference_autograd(golden):
     assert relmax(d, T(g["dtok"])) <= 1e-6
 
 
+# ------------------------------------------------------------------ trajectory head, generation side (8f item 4)
+def test_traj_inference_matches_reference(golden):
+    """oracle vs the reference's CVAETrajDecoder.inference (fixture froze its output and the noise it drew)."""
+    g = golden("traj_infer")
+    sd = synth.traj_cvae_state(32, seed=3)
+    emb = synth.gen("traj_emb", (3, 2, 4, 32), 1.0, seed=51)
+    out = restate.traj_decoder_inference(emb, T(g["z"]), sd)
+    assert out.shape == (3, 2, 4, 2)
+    assert float((out - T(g["out"])).abs().max()) <= 1e-6
+
+
+def test_traj_step_matches_reference(golden):
+    g = golden("traj_step")
+    sd = synth.traj_cvae_state(32, seed=3)
+    hidden_last = synth.gen("traj_hidden_last", (1, 64), 1.0, seed=52)
+    out = restate.traj_decode_step(hidden_last, T(g["z"]), sd)
+    assert out.shape == (1, 2, 2)
+    assert float((out - T(g["out"])).abs().max()) <= 1e-6
+
+
 # ------------------------------------------------------------------ gather (a7)
 @pytest.mark.parametrize("name,shape,seedname,seed", [
     ("gather_toy", None, None, None),

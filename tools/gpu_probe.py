@@ -347,9 +347,41 @@ def stage_hbm():
     print(f"layernorm 25700 rows: {ms * 1e3:7.1f} us  {25700 * 1024 * 6 / ms / 1e6:7.0f} GB/s", flush=True)
 
 
+def stage_traj():
+    """Fused gather + CVAE decoder step vs the same math as eager torch ops (what the reference's loop launches)."""
+    from hvlm_b200.traj_decoder import CVAETrajDecoder
+    for D in (4096, 5120):
+        dec = CVAETrajDecoder(token_dim=D // 2).to(dev).to(torch.bfloat16)
+        hl = torch.randn(1, D, device=dev).to(torch.bfloat16)
+        z = (2.0 * torch.randn(2, 256, device=dev)).to(torch.bfloat16)
+        d = dec.hand_traj_decoder.cvae.dec_MLP
+
+        def eager():
+            e = hl.reshape(1, D // 2, 2).permute(0, 2, 1).unsqueeze(2).reshape(-1, D // 2)
+            return d(torch.cat((z, e), dim=-1))
+
+        def fused():
+            return ops.traj_decode(hl, z, d[0].weight, d[0].bias, d[2].weight, d[2].bias, interleaved=True)
+
+        a, b = eager().float(), fused()
+        stats(f"traj step D={D} fused vs eager bf16", b, a)
+        for name, fn in (("eager", eager), ("fused", fused)):
+            g = torch.cuda.CUDAGraph()
+            fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                for _ in range(20):
+                    fn()
+            ms = _time(g.replay, 10) / 20
+            ms_host = _time(fn, 50)
+            print(f"traj step D={D} {name}: {ms * 1e3:6.2f} us/step device (graph replay), {ms_host * 1e3:6.1f} us/step "
+                  f"with host launch", flush=True)
+
+
 if __name__ == "__main__":
-    stage = sys.argv[1]
+  for stage in sys.argv[1:]:
     t0 = time.time()
+    RES.pop("exception", None)
     try:
         globals()["stage_" + stage]()
         torch.cuda.synchronize()
