@@ -481,6 +481,56 @@ def test_handsonvlm_path_end_to_end(tower23):
     assert int(host.last_visual_token_index) == 35 + 262
 
 
+def test_config3_full_size_16_clips_13b_shapes(tower23):
+    """BASELINE configs[2] at full size (16 clips x 100 frames, projector 1024->5120) through the drop-in interface,
+    checked by size-independent properties: (i) batch invariance -- a clip's visual tokens do not depend on what else is
+    in the batch, bit for bit; (ii) labels / mask are bit-exact against the oracle's splice of the same prompts;
+    (iii) in the spliced output the visual rows are exact copies of the tokens and the text rows exact copies of the
+    embedding-table rows (SURVEY 8a note i)."""
+    tw, sd = tower23("hf")
+    D, t, B = 5120, 100, 16
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    cfg = types.SimpleNamespace(fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool",
+                                mm_hidden_size=1024, input_type="video")
+    host = _host(arch.HandsOnVLMMetaForCausalLM, tw, proj.to(torch.bfloat16), emb.to(torch.bfloat16), cfg, B)
+    g = torch.Generator(device=DEV)
+    g.manual_seed(31)
+    px = torch.randn(B, t, 3, 224, 224, device=DEV, generator=g).to(torch.bfloat16)
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=B, seed=12)
+    with torch.no_grad():
+        r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px,
+                                                      future_hands=fh.to(DEV), future_valid=fv.to(DEV), is_evaluate=False)
+        helper = arch.VisualToTokenHelper(images_raw_encode=tw, images_mm_projector=host.get_model().mm_projector,
+                                          fuse_input_mode="origin", video_compress_mode="temporal_spatial_pool",
+                                          mm_hidden_size=1024, token_dim=D)
+        tok_all, vmask = helper.pipeline(images=px)
+        tok_5, _ = helper.pipeline(images=px[5:6])
+        tok_15, _ = helper.pipeline(images=px[15:16])
+    m2, e2, l2 = r[1], r[3], r[4]
+    T_in = ids.shape[1]
+    assert e2.shape == (B, T_in + 355, D) and tok_all.shape == (B, 356, D) and bool(vmask.all())
+    assert torch.equal(tok_all[5:6], tok_5) and torch.equal(tok_all[15:16], tok_15)
+    assert torch.isfinite(tok_all.float()).all()
+    # ints against the oracle (visual values do not influence them)
+    rm, _, rl = restate.splice(ids, mask, labels, torch.zeros(B, 356, 8), torch.zeros(synth.VOCAB, 8), "handsonvlm",
+                               future_hands=fh)
+    assert torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm)
+    # exact-copy rows
+    table = host.get_model().embed_tokens.weight
+    for b in (0, 7, 15):
+        start = int((ids[b] == -200).nonzero()[0])
+        assert torch.equal(e2[b, start:start + 356], tok_all[b])
+        assert torch.equal(e2[b, :start], table[ids[b, :start].to(DEV)])
+        tail_ids = ids[b, start + 1:].to(DEV)
+        plain = tail_ids != 32100                     # <hand_traj> rows carry the added GT-hand embedding
+        assert torch.equal(e2[b, start + 356:][plain], table[tail_ids[plain]])
+
+
 def test_llava_config1_single_image_fp32(tower23):
     """BASELINE config 1: single 224x224 image, fp32, 256 tokens -> projector 4096 -> LLaVA splice."""
     tw, sd = tower23("hf")
