@@ -139,10 +139,38 @@ __device__ __forceinline__ void ln_rows(const float* __restrict__ x, const float
     }
 }
 
+// Tile schedule of the persistent pairs.  The first `full` tiles (a whole number of waves) are 256 x 256; when the
+// leftover tiles would occupy at most half of the pairs, each of them is cut into two 256 x 128 half tiles so that the
+// last wave takes half the time (404 tiles on 74 pairs: 5.5 waves instead of 6).  A half tile runs the same K loop with
+// an N=128 MMA, so every output element sees the same accumulation order either way: results do not depend on the split.
+struct Sched {
+    int num_tiles, num_n, full, nv, split, reverse;
+    __device__ __forceinline__ Sched(int tiles, int n, int n_pairs, int allow_split, int rev)
+        : num_tiles(tiles), num_n(n), reverse(rev) {
+        full = (tiles / n_pairs) * n_pairs;
+        const int rem = tiles - full;
+        split = allow_split && rem > 0 && 2 * rem <= n_pairs;
+        nv = split ? full + 2 * rem : tiles;
+    }
+    // half = -1: whole tile; 0 / 1: left / right 128 columns
+    __device__ __forceinline__ void decode(int v, int& m_blk, int& n_blk, int& half) const {
+        int tile = v;
+        half = -1;
+        if (split && v >= full) {
+            tile = full + ((v - full) >> 1);
+            half = (v - full) & 1;
+        }
+        if (reverse) tile = num_tiles - 1 - tile;
+        m_blk = tile / num_n;
+        n_blk = tile - m_blk * num_n;
+    }
+};
+
 template <int EPI, bool LN, int G>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2) ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiArgs ep) {
+                     const __grid_constant__ CUtensorMap tma_bh, const __grid_constant__ CUtensorMap tma_c, int M, int N,
+                     int K, EpiArgs ep, int split_tail) {
     static_assert(epi_is_staged<EPI>(), "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
     static_assert(!(LN && G == 2), "the fused-LayerNorm warps and the second epilogue group use the same warp slots");
     constexpr int kStages = Cfg2<G>::kStages;
@@ -168,10 +196,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const int num_n = N / BN;
     const int num_tiles = num_m * num_n;
     const int num_kb = (K + BK - 1) / BK;
+    const Sched sched(num_tiles, num_n, n_pairs, LN ? 0 : split_tail, ep.reverse);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_bh);
         tma_prefetch_desc(&tma_c);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
@@ -196,19 +226,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         // ===================== TMA producer (both CTAs) =====================
         int stage = 0;
         uint32_t phase = 0;
-        for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
-            const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
-            const int m_blk = tile / num_n;
-            const int n_blk = tile - m_blk * num_n;
+        for (int v = pair; v < sched.nv; v += n_pairs) {
+            int m_blk, n_blk, half;
+            sched.decode(v, m_blk, n_blk, half);
             const int row_a = m_blk * 2 * BM + static_cast<int>(rank) * BM;
-            const int row_b = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+            // this CTA supplies its half of the tile's B rows: 128 of 256, or 64 of 128 for a half tile
+            const int row_b = half < 0 ? n_blk * BN + static_cast<int>(rank) * (BN / 2)
+                                       : n_blk * BN + half * (BN / 2) + static_cast<int>(rank) * (BN / 4);
+            const CUtensorMap* tb = half < 0 ? &tma_b : &tma_bh;
+            const uint32_t tx = half < 0 ? 2u * kStageBytes : 2u * (kABytes + kBBytes / 2);
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1u);
                 if (elect_one()) {
                     // the leader arms its barrier with the bytes of BOTH CTAs; the peer's loads complete on it too
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
                     tma_load_2d_2sm(smem_a + stage * kABytes, &tma_a, &full_bar[stage], kb * BK, row_a);
-                    tma_load_2d_2sm(smem_b + stage * kBBytes, &tma_b, &full_bar[stage], kb * BK, row_b);
+                    tma_load_2d_2sm(smem_b + stage * kBBytes, tb, &full_bar[stage], kb * BK, row_b);
                 }
                 __syncwarp();
                 if (++stage == kStages) {
@@ -220,12 +253,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            constexpr uint32_t idesc_whole = umma_idesc_bf16(2 * BM, BN);
+            constexpr uint32_t idesc_half = umma_idesc_bf16(2 * BM, BN / 2);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
+            for (int v = pair; v < sched.nv; v += n_pairs) {
+                const uint32_t idesc = (sched.split && v >= sched.full) ? idesc_half : idesc_whole;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -264,8 +299,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         uint32_t acc_phase = 0;
         constexpr bool kF32 = epi_out_f32<EPI>();
         constexpr int kUnitCols = kF32 ? 32 : 64;
-        constexpr int kUnits = BN / kUnitCols / G;          // units per group
-        const int u0 = grp * kUnits;                        // first unit of this group
+        constexpr int kUnits = BN / kUnitCols / G;          // units per group (whole tile)
+        static_assert(kUnits >= 2, "half tiles need at least one unit per group");
         const int row = q * 32 + lane;
         const int sw = row & 7;
         const bool store_warp = (((warp - 2) & 3) == 0);
@@ -273,16 +308,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
         uint32_t ucount = 0;
         int pending_rb = -1;
-        for (int t_ = pair; t_ < num_tiles; t_ += n_pairs) {
-            const int tile = ep.reverse ? num_tiles - 1 - t_ : t_;
-            const int m_blk = tile / num_n;
-            const int n_blk = tile - m_blk * num_n;
+        for (int v = pair; v < sched.nv; v += n_pairs) {
+            int m_blk, n_blk, half;
+            sched.decode(v, m_blk, n_blk, half);
             const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+            // a half tile has half the column units; its accumulator sits in the first 128 TMEM columns of the buffer
+            const int units = half < 0 ? kUnits : kUnits / 2;
+            const int u0 = grp * units;
+            const int ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-            for (int uu = 0; uu < kUnits; ++uu, ++ucount) {
+            for (int uu = 0; uu < units; ++uu, ++ucount) {
                 const int u = u0 + uu;
                 uint8_t* buf = smem_cg + (ucount & 1u) * kStoreBuf;
                 uint8_t* brow = buf + row * 128;
@@ -291,7 +329,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     __syncwarp();
                 }
                 named_bar_sync(bar_a, 128);
-                const int n0 = n_blk * BN + u * kUnitCols;
+                const int n0 = ncol0 + u * kUnitCols;
 #pragma unroll
                 for (int h = 0; h < kUnitCols / 32; ++h) {
                     uint32_t r[32];
@@ -316,7 +354,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         }
                     }
                 }
-                if (uu == kUnits - 1) {
+                if (uu == units - 1) {
                     // last TMEM read of this accumulator by this group: release it to the (leader's) MMA warp
                     tc_fence_before();
                     if (rank == 0) mbar_arrive(&tempty_bar[acc]);
@@ -406,7 +444,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 
 template <int EPI, bool LN = false, int G = 1>
 static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
-    CUtensorMap ta, tb, tc;
+    CUtensorMap ta, tb, tbh, tc;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
         uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
@@ -419,6 +457,13 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
         uint32_t box[2] = {BK, BN / 2};
         int rc = make_tmap_bf16(&tb, B, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+        uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+        uint32_t box[2] = {BK, BN / 4};               // half tiles: 64 B rows per CTA
+        int rc = make_tmap_bf16(&tbh, B, 2, dims, str, box);
         if (rc) return rc;
     }
     {
@@ -449,10 +494,18 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
             return HVLM_ERR_CUDA;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
+    // HVLM_GEMM_TAIL_SPLIT=0 keeps whole tiles in the last wave (A/B runs)
+    static const int split_tail = []() {
+        const char* e = getenv("HVLM_GEMM_TAIL_SPLIT");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    const int allow_split = LN ? 0 : split_tail;
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN);
     int pairs = num_sms() / 2;
-    if (tiles < pairs) pairs = tiles;
-    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + ((LN || G == 2) ? 128 : 0)), kSmemBytes, s, ta, tb, tc, M, N, K, ep) != cudaSuccess) {
+    const int want = allow_split ? 2 * tiles : tiles;      // few tiles: cut all of them in two to occupy more pairs
+    if (want < pairs) pairs = want;
+    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + ((LN || G == 2) ? 128 : 0)), kSmemBytes, s, ta, tb, tbh, tc, M, N, K, ep,
+                   allow_split) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
     }

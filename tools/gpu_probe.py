@@ -378,6 +378,27 @@ def stage_traj():
                   f"with host launch", flush=True)
 
 
+def stage_latency():
+    """Small-batch tower latency (configs[0]: one image): stream launches vs one CUDA-graph replay."""
+    import types as _t
+    from hvlm_b200.tower import CLIPVisionTower
+    sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=23)
+    tw = CLIPVisionTower("synthetic", _t.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    tw.load_model(sd)
+    tw = tw.to(dev)
+    for n in (1, 2, 4, 10, 20):
+        px = torch.randn(n, 3, 224, 224, device=dev)
+        fn = lambda: tw(px)
+        ms = _time(fn, 20)
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            out = fn()
+        ms_g = _time(g.replay, 20)
+        print(f"tower N={n:3d}: {ms:7.3f} ms stream launches, {ms_g:7.3f} ms graph replay", flush=True)
+        RES[f"latency_{n}"] = {"stream_ms": ms, "graph_ms": ms_g}
+
+
 if __name__ == "__main__":
   for stage in sys.argv[1:]:
     t0 = time.time()
