@@ -7,17 +7,22 @@
 //
 // Design (sized so that TWO CTAs are resident per SM: one CTA's MMAs overlap the other's softmax):
 //   * 257 = 256 + 1.  The tensor cores handle the 256 x 256 block (queries/keys 0..255) as two 128-row tiles.
-//     The 257th KEY is folded in on CUDA cores by the softmax threads (one 64-MAC dot product per row and one extra
-//     term in max / sum / output).  The 257th QUERY row is computed on CUDA cores: its 257 scores by the softmax
-//     threads (two dot products each, in the shadow of the first S MMA), its softmax and P*V by a dedicated warp.
+//     The scores that involve token 256 also come from the tensor cores, as four N=16 MMAs per item against 16-row
+//     tiles that start at row 256 (row 0 of the tile is the token, the other rows are ignored):
+//        Q_tile0/1 x Ktail^T -> score of every query against the 257th key
+//        K_tile0/1 x Qtail^T -> score of the 257th query against every key (lane = key)
+//     They are issued for the NEXT item while the current item's last P*V runs, into TMEM columns whose S values are
+//     already dead, and every softmax thread picks its four values up right before it releases the accumulator.
+//     The 257th key then costs one extra term in max / sum / output; the 257th query's softmax and P*V (257 x 64 MACs)
+//     run on the CUDA cores of the four softmax warps (64 keys each) while they wait for the first P*V MMA.
 //   * TMEM: 256 columns per CTA.  S[128x256] fp32 fills them; the un-normalised probabilities are written back
 //     IN PLACE as packed bf16 (P aliases columns 0..127, tcgen05.st) and feed the second MMA as a TMEM A-operand;
-//     O[128x64] accumulates in columns 128..191.
-//   * smem (109 KB): Q (2 tiles) | K[256x64] | V[256x64] | row 256 of q,k,v | tail-query scratch | per-warp store
-//     staging.  V is consumed as an MN-major B operand (no transpose anywhere).
+//     O[128x64] accumulates in columns 128..191; the token-256 score blocks use columns 192..255.
+//   * smem (109 KB): Q (2 tiles) | K[256x64] | V[256x64] | 16-row tail tiles of q,k | row 256 of v | tail-query
+//     scratch | per-warp store staging.  V is consumed as an MN-major B operand (no transpose anywhere).
 //   * warps: 0 = TMA + MMA issue (warp-uniform control flow, one elected lane issues), 1..4 = softmax + epilogue
-//     (one query row per thread, fp32), 5 = tail query.  Output rows are transposed through a small per-warp smem
-//     buffer so that every global store instruction writes four full 128-byte lines.
+//     (one query row per thread, fp32).  Output rows are transposed through a small per-warp smem buffer so that
+//     every global store instruction writes four full 128-byte lines.
 //   * next item's Q/K (V) loads are issued as soon as the current item's last S (PV) MMA has retired and the
 //     CUDA-core readers of that buffer have signalled.
 #include "hvlm_internal.cuh"
@@ -26,23 +31,29 @@
 namespace hvlm {
 namespace attn {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 160;
 constexpr int kS = HVLM_VIT_TOKENS;        // 257
 constexpr int kTile = 128 * 64 * 2;        // 16384 : one [128 x 64] bf16 operand tile
+constexpr int kTailTile = 16 * 128;        // 2048  : rows 256..271 of q / k (row 0 = token 256; N=16 MMA operand)
 constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + 2 * kTile;
 constexpr int kOffV = kOffK + 2 * kTile;
-constexpr int kOffQT = kOffV + 2 * kTile;  // q row 256 (128 B used; 1 KB slot keeps the swizzle phase at 0)
-constexpr int kOffKT = kOffQT + 1024;      // k row 256
-constexpr int kOffVT = kOffKT + 1024;      // v row 256
-constexpr int kOffStage = kOffVT + 1024;   // 4 warps x 2 KB output staging
-constexpr int kOffPT = kOffStage + 4 * 2048;   // 2 x float[272]: scores / probabilities of the tail query
-constexpr int kOffBar = kOffPT + 2 * 272 * 4;
+constexpr int kOffQT = kOffV + 2 * kTile;  // q rows 256..271
+constexpr int kOffKT = kOffQT + kTailTile; // k rows 256..271
+constexpr int kOffVT = kOffKT + kTailTile; // v row 256 (128 B used; 1 KB slot keeps the swizzle phase at 0)
+constexpr int kOffStage = kOffVT + 1024;   // 4 warps x 1 KB output staging
+constexpr int kOffPT = kOffStage + 4 * 1024;   // float[272] scores + float[272] probabilities of the tail query
+constexpr int kOffPart = kOffPT + 2 * 272 * 4; // float[4][64]: per-warp partial P*V of the tail query
+constexpr int kOffBar = kOffPart + 4 * 64 * 4;
 constexpr int kSmem = kOffBar + 128 + 1024;    // + barriers + alignment slack
-constexpr uint32_t kQKTx = 4 * kTile + 2 * 128;
+static_assert(2 * (kSmem + 1024) <= 228 * 1024, "two CTAs must fit in one SM's shared memory");
+constexpr uint32_t kQKTx = 4 * kTile + 2 * kTailTile;
 constexpr uint32_t kVTx = 2 * kTile + 128;
 constexpr int kPCol = 0;                   // P (bf16 pairs) : TMEM columns [0,128)
 constexpr int kOCol = 128;                 // O accumulator  : TMEM columns [128,192)
+constexpr int kTCol = 192;                 // token-256 score blocks, 16 columns each (column 0 used):
+                                           //   +0 / +16 : queries of tile 0 / 1 against key 256
+                                           //   +32 / +48: query 256 against keys of tile 0 / 1 (lane = key)
 
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -63,6 +74,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {   // valid after tmem_ld_wait()
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -78,39 +92,43 @@ __device__ __forceinline__ void unpack8(const uint4& w, float* f) {
         f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
     }
 }
-// dot product of row `row` of a SWIZZLE_128B [rows x 64] bf16 tile with a 64-float vector held in registers
-__device__ __forceinline__ float dot_row64(const uint8_t* tile, int row, const float (&vec)[64]) {
-    const uint8_t* base = tile + row * 128;
-    const int sw = row & 7;
-    float acc0 = 0.f, acc1 = 0.f;
+__device__ __forceinline__ void max_chunk32(const uint32_t (&v)[32], float& m) {
+    float a = m, b = m;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(base + ((j ^ sw) << 4)), f);
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-            acc0 = fmaf(f[i], vec[8 * j + i], acc0);
-            acc1 = fmaf(f[i + 1], vec[8 * j + i + 1], acc1);
-        }
+    for (int j = 0; j < 32; j += 4) {
+        a = fmaxf(a, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+        b = fmaxf(b, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
     }
-    return acc0 + acc1;
+    m = fmaxf(a, b);
 }
-// a single 128-byte row stored at a 1024-aligned address (swizzle phase 0 -> chunks in natural order) -> 64 floats
-__device__ __forceinline__ void load_row0(const uint8_t* row, float (&vec)[64]) {
+// p = 2^(s*log2e - mxl) for one 32-column chunk; packed bf16 pairs; returns the chunk's sum
+__device__ __forceinline__ float exp_chunk32(const uint32_t (&v)[32], float log2e, float mxl, uint32_t (&pk)[16]) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) unpack8(*reinterpret_cast<const uint4*>(row + (j << 4)), &vec[8 * j]);
+    for (int j = 0; j < 16; j += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), log2e, -mxl));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), log2e, -mxl));
+        const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 2]), log2e, -mxl));
+        const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 3]), log2e, -mxl));
+        s0 += p0 + p1;
+        s1 += p2 + p3;
+        pk[j] = pack_bf16(p0, p1);
+        pk[j + 1] = pack_bf16(p2, p3);
+    }
+    return s0 + s1;
 }
 
 // debug: per-phase timestamps (trace == nullptr in production)
 #define ATTN_TRACE(role, slot)                                                                          \
     do {                                                                                                \
         if (trace != nullptr && it < 4)                                                                 \
-            trace[((static_cast<size_t>(blockIdx.x) * 2 + (role)) * 4 + it) * 16 + (slot)] = clock64();   \
+            trace[((static_cast<size_t>(blockIdx.x) * 5 + (role)) * 4 + it) * 16 + (slot)] = clock64();   \
     } while (0)
 
 __global__ void __launch_bounds__(kThreads, 2)
-attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail,
-                    __nv_bfloat16* __restrict__ out, int n_items, long long* __restrict__ trace) {
+attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail16,
+                    const __grid_constant__ CUtensorMap tm_tail1, __nv_bfloat16* __restrict__ out, int n_items,
+                    long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -121,18 +139,20 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     uint8_t* sKT = smem + kOffKT;
     uint8_t* sVT = smem + kOffVT;
     uint8_t* sStage = smem + kOffStage;
-    float* sPT = reinterpret_cast<float*>(smem + kOffPT);
+    float* sSc = reinterpret_cast<float*>(smem + kOffPT);          // scores of the tail query: [0..255] keys, [256] key 256
+    float* sPp = sSc + 272;                                        // its un-normalised probabilities (keys 0..255)
+    float* sPart = reinterpret_cast<float*>(smem + kOffPart);      // [4 warps][64 dims]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint64_t* qk_full = bars + 0;    // TMA  -> everyone        (once per item)
-    uint64_t* v_full = bars + 1;     // TMA  -> MMA, tail warp  (once per item)
+    uint64_t* v_full = bars + 1;     // TMA  -> MMA, softmax    (once per item)
     uint64_t* s_full = bars + 2;     // MMA  -> softmax         (once per tile)
     uint64_t* p_full = bars + 3;     // softmax(128) -> MMA     (once per tile)
     uint64_t* o_full = bars + 4;     // MMA  -> softmax         (once per tile)
-    uint64_t* o_read = bars + 5;     // softmax(128) -> MMA     (once per tile): O left TMEM, S region reusable
-    uint64_t* q_read = bars + 6;     // softmax(128) -> MMA, tail warp (once per item): Q/K rows consumed by the
-                                     //   CUDA cores, tail-query scores published
-    uint64_t* tv_done = bars + 7;    // tail warp -> MMA        (once per item): V consumed by the tail warp
-    uint64_t* vt_read = bars + 8;    // softmax(128) -> MMA     (once per item): v row 256 consumed by the epilogues
+    uint64_t* o_read = bars + 5;     // softmax(128) -> MMA     (once per tile): O (and, on the item's last tile, the
+                                     //   next item's token-256 scores) left TMEM, S region reusable
+    uint64_t* t_full = bars + 6;     // MMA  -> softmax         (once per item): token-256 score blocks written
+    uint64_t* t_read = bars + 7;     // softmax(128) -> MMA     (once, first item only): those blocks were read
+    uint64_t* vt_read = bars + 8;    // softmax(128) -> MMA     (once per item): V / v row 256 consumed by the CUDA cores
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5;
@@ -141,15 +161,16 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&tm_qkv);
-            tma_prefetch_desc(&tm_tail);
+            tma_prefetch_desc(&tm_tail16);
+            tma_prefetch_desc(&tm_tail1);
             mbar_init(qk_full, 1);
             mbar_init(v_full, 1);
             mbar_init(s_full, 1);
             mbar_init(p_full, 128);
             mbar_init(o_full, 1);
             mbar_init(o_read, 128);
-            mbar_init(q_read, 128);
-            mbar_init(tv_done, 1);
+            mbar_init(t_full, 1);
+            mbar_init(t_read, 128);
             mbar_init(vt_read, 128);
             fence_mbar_init();
         }
@@ -166,10 +187,13 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (warp == 0) {
         // ===================== TMA producer + MMA issuer =====================
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+        constexpr uint32_t idesc_t = umma_idesc_bf16(128, 16);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, /*b_mn_major=*/1);
         const uint64_t dQ = umma_desc_k_sw128(smem_u32(sQ));
         const uint64_t dK = umma_desc_k_sw128(smem_u32(sK));
         const uint64_t dV = umma_desc_k_sw128(smem_u32(sV));
+        const uint64_t dQT = umma_desc_k_sw128(smem_u32(sQT));
+        const uint64_t dKT = umma_desc_k_sw128(smem_u32(sKT));
 
         // item = frame*16 + head; column blocks: q -> head, k -> 16+head, v -> 32+head
         auto load_qk = [&](int item) {
@@ -178,10 +202,10 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_arrive_expect_tx(qk_full, kQKTx);
                 tma_load_3d(sQ, &tm_qkv, qk_full, 0, r0, h);
                 tma_load_3d(sQ + kTile, &tm_qkv, qk_full, 0, r0 + 128, h);
-                tma_load_3d(sQT, &tm_tail, qk_full, 0, r0 + 256, h);
+                tma_load_3d(sQT, &tm_tail16, qk_full, 0, r0 + 256, h);
                 tma_load_3d(sK, &tm_qkv, qk_full, 0, r0, 16 + h);
                 tma_load_3d(sK + kTile, &tm_qkv, qk_full, 0, r0 + 128, 16 + h);
-                tma_load_3d(sKT, &tm_tail, qk_full, 0, r0 + 256, 16 + h);
+                tma_load_3d(sKT, &tm_tail16, qk_full, 0, r0 + 256, 16 + h);
             }
             __syncwarp();
         };
@@ -191,7 +215,35 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 mbar_arrive_expect_tx(v_full, kVTx);
                 tma_load_3d(sV, &tm_qkv, v_full, 0, r0, 32 + h);
                 tma_load_3d(sV + kTile, &tm_qkv, v_full, 0, r0 + 128, 32 + h);
-                tma_load_3d(sVT, &tm_tail, v_full, 0, r0 + 256, 32 + h);
+                tma_load_3d(sVT, &tm_tail1, v_full, 0, r0 + 256, 32 + h);
+            }
+            __syncwarp();
+        };
+        // the four token-256 score blocks of the item whose Q / K are in shared memory
+        auto issue_tail = [&]() {
+            if (elect_one()) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint64_t da = (b < 2 ? dQ : dK) + static_cast<uint64_t>(((b & 1) * kTile) >> 4);
+                    const uint64_t db = b < 2 ? dKT : dQT;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_base + kTCol + b * 16, da + static_cast<uint64_t>(2 * k),
+                                     db + static_cast<uint64_t>(2 * k), idesc_t, k > 0);
+                }
+                umma_commit(t_full);
+            }
+            __syncwarp();
+        };
+
+        auto issue_s = [&](int tile) {
+            // S = Q_tile K^T : 4 k-steps over the 64 head dims, N = 256 keys
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base, dQ + static_cast<uint64_t>((tile * kTile) >> 4) + static_cast<uint64_t>(2 * k),
+                                 dK + static_cast<uint64_t>(2 * k), idesc_s, k > 0);
+                umma_commit(s_full);
             }
             __syncwarp();
         };
@@ -202,33 +254,30 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (static_cast<int>(blockIdx.x) < n_items) {
             load_qk(n_items - 1 - blockIdx.x);
             load_v(n_items - 1 - blockIdx.x);
+            mbar_wait(qk_full, 0);
+            tc_fence_after();
+            issue_tail();
+            mbar_wait(t_read, 0);    // the softmax threads hold the first item's token-256 scores in registers
+            tc_fence_after();
+            issue_s(0);
         }
         for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++it) {
             const int next_idx = idx + gridDim.x;
             const int next = n_items - 1 - next_idx;
             if (lane == 0) ATTN_TRACE(0, 0);
-            mbar_wait(qk_full, it & 1);
-            if (lane == 0) ATTN_TRACE(0, 1);
             for (int tile = 0; tile < 2; ++tile, ++n2) {
-                // the S region doubles as P / O storage of the previous tile: wait until its O has been read
-                if (n2 > 0) mbar_wait(o_read, (n2 - 1) & 1);
-                if (lane == 0) ATTN_TRACE(0, 2 + tile * 6);
-                tc_fence_after();
-                // S = Q_tile K^T : 4 k-steps over the 64 head dims, N = 256 keys
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_base, dQ + static_cast<uint64_t>((tile * kTile) >> 4) + static_cast<uint64_t>(2 * k),
-                                     dK + static_cast<uint64_t>(2 * k), idesc_s, k > 0);
-                    umma_commit(s_full);
-                }
-                __syncwarp();
                 if (tile == 1) {
-                    // Q / K smem is free once the last S MMA has retired and the CUDA-core readers are done
+                    // the S region doubles as P / O storage of the previous tile: wait until its O has been read
+                    mbar_wait(o_read, (n2 - 1) & 1);
+                    if (lane == 0) ATTN_TRACE(0, 2 + tile * 6);
+                    tc_fence_after();
+                    issue_s(1);
+                    // Q / K smem is free once the last S MMA has retired (the token-256 blocks retired long ago, and
+                    // the CUDA-core read of the two tail rows happened before this item's first p_full arrival)
                     mbar_wait(s_full, n2 & 1);
-                    mbar_wait(q_read, it & 1);
                     if (next_idx < n_items) load_qk(next);
                 }
+                // (tile 0: its S MMAs were issued at the end of the previous item / in the prologue)
                 if (lane == 0) ATTN_TRACE(0, 3 + tile * 6);
                 mbar_wait(p_full, n2 & 1);
                 if (lane == 0) ATTN_TRACE(0, 4 + tile * 6);
@@ -246,108 +295,200 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 __syncwarp();
                 if (lane == 0) ATTN_TRACE(0, 5 + tile * 6);
             }
+            if (next_idx < n_items) {
+                // S columns 192..255 are dead (every softmax thread passed p_full): the next item's token-256
+                // blocks go there, behind the P*V in the tensor pipe; the softmax threads read them before they signal
+                // o_read, and then the next item's first S tile can start while this item's epilogue is still running
+                mbar_wait(qk_full, (it + 1) & 1);
+                tc_fence_after();
+                issue_tail();
+                mbar_wait(o_read, (n2 - 1) & 1);
+                tc_fence_after();
+                issue_s(0);
+            }
             // PV of the last tile retired and the CUDA-core readers are done with V -> V smem is free
             mbar_wait(o_full, (n2 - 1) & 1);
-            mbar_wait(tv_done, it & 1);
             mbar_wait(vt_read, it & 1);
             if (lane == 0) ATTN_TRACE(0, 14);
             if (next_idx < n_items) load_v(next);
         }
-    } else if (warp <= 4) {
+    } else {
         // ===================== softmax + epilogue warps: one query row per thread =====================
         const int q = warp & 3;                       // TMEM lane quarter
         const int r = q * 32 + lane;                  // row inside the 128-row tile
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        uint8_t* stage = sStage + (warp - 1) * 2048;  // this warp's 16-row x 128-byte transpose buffer
+        uint8_t* stage = sStage + (warp - 1) * 1024;  // this warp's 8-row x 128-byte transpose buffer
         constexpr float kLog2e = 1.4426950408889634f;
         uint32_t n2 = 0;
         int it = 0;
+        uint32_t tl[4] = {0u, 0u, 0u, 0u};             // token-256 scores of the upcoming item (see kTCol)
+        if (static_cast<int>(blockIdx.x) < n_items) {
+            mbar_wait(t_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tmem_ld1(t_lane + kTCol + b * 16, tl[b]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(t_read);
+        }
         for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++it) {
             const int item = n_items - 1 - idx;
             const int f = item >> 4, head = item & 15;
-            const bool tr = (r == 0);
-            if (tr) ATTN_TRACE(1, 0);
+            const bool has_next = idx + static_cast<int>(gridDim.x) < n_items;
+            const bool tr = (lane == 0);
+            if (tr) ATTN_TRACE(warp, 0);
+            const float s_tail[2] = {__uint_as_float(tl[0]), __uint_as_float(tl[1])};
+            sSc[r] = __uint_as_float(tl[2]);
+            sSc[r + 128] = __uint_as_float(tl[3]);
             mbar_wait(qk_full, it & 1);
-            if (tr) ATTN_TRACE(1, 1);
-            // ---- CUDA-core side work, in the shadow of the first S MMA:
-            //      (a) this thread's two query rows against the 257th key, (b) the 257th query against this thread's
-            //      two key rows (scores of the tail query, published through smem to the tail warp)
-            float s_tail[2];
-            {
-                float vec[64];
-                load_row0(sKT, vec);
-                s_tail[0] = dot_row64(sQ, r, vec);
-                s_tail[1] = dot_row64(sQ + kTile, r, vec);
-                float* pt = sPT + (it & 1) * 272;
-                if (tr) {   // q_256 . k_256 needs both tail rows: do it before vec is overwritten
-                    float kt_dot = 0.f;
+            if (tr) ATTN_TRACE(warp, 1);
+            if (q == 1) {   // q_256 . k_256: two dims per lane (row 0 of a 1024-aligned tile: natural chunk order)
+                const uint32_t qa = *reinterpret_cast<const uint32_t*>(sQT + lane * 4);
+                const uint32_t ka = *reinterpret_cast<const uint32_t*>(sKT + lane * 4);
+                float d = __uint_as_float(qa << 16) * __uint_as_float(ka << 16) +
+                          __uint_as_float(qa & 0xFFFF0000u) * __uint_as_float(ka & 0xFFFF0000u);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float qv[8];
-                        unpack8(*reinterpret_cast<const uint4*>(sQT + (j << 4)), qv);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) kt_dot = fmaf(qv[i], vec[8 * j + i], kt_dot);
-                    }
-                    pt[256] = kt_dot;
-                }
-                load_row0(sQT, vec);
-                pt[r] = dot_row64(sK, r, vec);
-                pt[r + 128] = dot_row64(sK + kTile, r, vec);
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (lane == 0) sSc[256] = d;
             }
-            mbar_arrive(q_read);
+            float tq_inv = 0.f, tq_p256 = 0.f;          // tail query: 1 / rowsum and its weight on key 256
             for (int tile = 0; tile < 2; ++tile, ++n2) {
-                if (tr) ATTN_TRACE(1, 2 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 2 + tile * 7);
                 mbar_wait(s_full, n2 & 1);
-                if (tr) ATTN_TRACE(1, 3 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 3 + tile * 7);
                 tc_fence_after();
-                // ---- pass 1: row max over 256 keys (TMEM) and the tail key
-                float mx = s_tail[tile];
+                // ---- pass 1: row max over 256 keys (TMEM) and the tail key.  Two register buffers: the next chunk's
+                //      tcgen05.ld is in flight while the current one is reduced.
+                //      Three tcgen05.ld (96 columns) are in flight per round trip, independent running maxima.
+                float mx;
+                {
+                    float m0 = s_tail[tile], m1 = m0, m2 = m0, m3 = m0;
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-                }
-                if (tr) ATTN_TRACE(1, 4 + tile * 7);
-                // ---- pass 2: p = exp(s - max) (fp32), row sum, P -> packed bf16 back into TMEM (aliases S)
-                const float mxl = mx * kLog2e;
-                float sum = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane + c * 32, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), kLog2e, -mxl));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), kLog2e, -mxl));
-                        sum += p0 + p1;
-                        pk[j] = pack_bf16(p0, p1);
+                    for (int c0 = 0; c0 < 256; c0 += 96) {          // columns [0,96) [96,192) [192,256)
+                        uint32_t v0[32], v1[32], v2[32];
+                        tmem_ld32(t_lane + c0, v0);
+                        tmem_ld32(t_lane + c0 + 32, v1);
+                        if (c0 < 192) tmem_ld32(t_lane + c0 + 64, v2);
+                        tmem_ld_wait();
+                        max_chunk32(v0, m0);
+                        max_chunk32(v1, m1);
+                        if (c0 < 192) max_chunk32(v2, m2);
                     }
-                    tmem_st16(t_lane + kPCol + c * 16, pk);
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                }
+                if (tr) ATTN_TRACE(warp, 4 + tile * 7);
+                // ---- pass 2: p = exp(s - max) (fp32), row sum, P -> packed bf16 back into TMEM (aliases S; chunk c's
+                //      16 P columns land in S columns that were already consumed)
+                const float mxl = mx * kLog2e;
+                float sum = 0.f, sum1 = 0.f;
+                {
+                    uint32_t va[32], vb[32], pk[16];
+                    tmem_ld32(t_lane, va);
+#pragma unroll 1
+                    for (int c = 0; c < 8; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(t_lane + (c + 1) * 32, vb);
+                        sum += exp_chunk32(va, kLog2e, mxl, pk);
+                        tmem_st16(t_lane + kPCol + c * 16, pk);
+                        tmem_ld_wait();
+                        if (c + 2 < 8) tmem_ld32(t_lane + (c + 2) * 32, va);
+                        sum1 += exp_chunk32(vb, kLog2e, mxl, pk);
+                        tmem_st16(t_lane + kPCol + (c + 1) * 16, pk);
+                    }
                 }
                 const float p_tail = fast_exp2(fmaf(s_tail[tile], kLog2e, -mxl));
-                sum += p_tail;
+                sum += sum1 + p_tail;
                 const float inv_sum = 1.0f / sum;
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(p_full);
-                if (tr) ATTN_TRACE(1, 5 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 5 + tile * 7);
+
+                // ---- the 257th query row on CUDA cores, in the shadow of the P*V MMAs
+                if (tile == 0) {
+                    // softmax of its 257 scores (every warp redundantly) and P*V over this warp's 64 keys
+                    named_bar_sync(1, 128);            // all scores are in sSc
+                    mbar_wait(v_full, it & 1);         // V / v row 256 are read by the CUDA cores from here on
+                    const float s256 = sSc[256];
+                    float sc[8];
+                    float tmx = s256;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        sc[j] = sSc[lane + 32 * j];
+                        tmx = fmaxf(tmx, sc[j]);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tmx = fmaxf(tmx, __shfl_xor_sync(0xffffffffu, tmx, o));
+                    tq_p256 = __expf(s256 - tmx);
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float p = __expf(sc[j] - tmx);
+                        tsum += p;
+                        if ((j >> 1) == q) sPp[lane + 32 * j] = p;   // keys 64q .. 64q+63 belong to this warp
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+                    tq_inv = 1.0f / (tsum + tq_p256);
+                } else {
+                    // P*V over this warp's 64 keys (its own probabilities: no cross-warp dependency), then combine
+                    __syncwarp();
+                    const int g = lane >> 3;           // 16 keys per lane group
+                    const int c = lane & 7;            // 16-byte chunk of the head dim: dims 8c .. 8c+7
+                    float acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const int key = q * 64 + g * 16 + kk;
+                        const uint8_t* rowp = (key < 128 ? sV : sV + kTile) + (key & 127) * 128;
+                        float vv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(rowp + ((c ^ (key & 7)) << 4)), vv);
+                        const float p = sPp[key];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vv[i], acc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+                        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+                    }
+                    if (g == 0) {
+                        float4* dst = reinterpret_cast<float4*>(sPart + q * 64 + c * 8);
+                        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    }
+                    named_bar_sync(2, 128);            // the four partial sums are in sPart
+                    if (q == 1) {
+                        const int d = 2 * lane;
+                        const uint32_t va = *reinterpret_cast<const uint32_t*>(sVT + lane * 4);
+                        const float o0 = (sPart[d] + sPart[64 + d]) + (sPart[128 + d] + sPart[192 + d]) +
+                                         tq_p256 * __uint_as_float(va << 16);
+                        const float o1 = (sPart[d + 1] + sPart[64 + d + 1]) + (sPart[128 + d + 1] + sPart[192 + d + 1]) +
+                                         tq_p256 * __uint_as_float(va & 0xFFFF0000u);
+                        *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(f) * kS + 256) * 1024 + head * 64 + d) =
+                            pack_bf16(o0 * tq_inv, o1 * tq_inv);
+                    }
+                }
 
                 // ---- epilogue: (O + p_tail * v_256) / rowsum -> bf16
                 mbar_wait(o_full, n2 & 1);
-                if (tr) ATTN_TRACE(1, 6 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 6 + tile * 7);
                 tc_fence_after();
                 uint32_t o0[32], o1[32];
                 tmem_ld32(t_lane + kOCol, o0);
                 tmem_ld32(t_lane + kOCol + 32, o1);
+                if (tile == 1 && has_next) {
+                    // the next item's token-256 scores were written right behind this P*V
+                    mbar_wait(t_full, (it + 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tmem_ld1(t_lane + kTCol + b * 16, tl[b]);
+                }
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(o_read);
-                if (tr) ATTN_TRACE(1, 7 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 7 + tile * 7);
                 uint4 rowv[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -362,97 +503,28 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                     rowv[j].z = pack_bf16(y[4], y[5]);
                     rowv[j].w = pack_bf16(y[6], y[7]);
                 }
-                // transpose through the per-warp staging buffer (16 rows at a time) so that each global store
+                // transpose through the per-warp staging buffer (8 rows at a time) so that each global store
                 // instruction writes 4 complete 128-byte rows: lane L -> row L/8 + 4i, 16-byte chunk L%8
                 const size_t row0 = static_cast<size_t>(f) * kS + tile * 128 + q * 32;
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    if ((lane >> 4) == half) {
-                        uint8_t* srow = stage + (lane & 15) * 128;
+                for (int part = 0; part < 4; ++part) {
+                    if ((lane >> 3) == part) {
+                        uint8_t* srow = stage + (lane & 7) * 128;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) = rowv[j];
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < 2; ++i) {
                         const int rr = (lane >> 3) + 4 * i;
                         const uint4 w = *reinterpret_cast<const uint4*>(stage + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-                        *reinterpret_cast<uint4*>(out + (row0 + half * 16 + rr) * 1024 + head * 64 + (lane & 7) * 8) = w;
+                        *reinterpret_cast<uint4*>(out + (row0 + part * 8 + rr) * 1024 + head * 64 + (lane & 7) * 8) = w;
                     }
                     __syncwarp();
                 }
-                if (tr) ATTN_TRACE(1, 8 + tile * 7);
+                if (tr) ATTN_TRACE(warp, 8 + tile * 7);
             }
             mbar_arrive(vt_read);
-        }
-    } else {
-        // ===================== warp 5: softmax and P*V of the 257th query row on CUDA cores =====================
-        const int g = lane >> 3;      // key group: keys 64g .. 64g+63
-        const int c = lane & 7;       // 16-byte chunk of the head dim: dims 8c .. 8c+7
-        int it = 0;
-        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++it) {
-            const int item = n_items - 1 - idx;
-            const int f = item >> 4, head = item & 15;
-            float* pt = sPT + (it & 1) * 272;
-            mbar_wait(q_read, it & 1);          // scores published by the softmax threads
-            float sc[8];
-            float mx = pt[256];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sc[j] = pt[lane + 32 * j];
-                mx = fmaxf(mx, sc[j]);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float p256 = __expf(pt[256] - mx);
-            __syncwarp();                        // every lane has read pt[256] / its scores before p overwrites them
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float p = __expf(sc[j] - mx);
-                sum += p;
-                pt[lane + 32 * j] = p;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            sum += p256;
-            __syncwarp();
-            mbar_wait(v_full, it & 1);
-            float acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-            for (int kk = 0; kk < 64; ++kk) {
-                const int key = g * 64 + kk;
-                const uint8_t* rowp = (key < 128 ? sV : sV + kTile) + (key & 127) * 128;
-                float vv[8];
-                unpack8(*reinterpret_cast<const uint4*>(rowp + ((c ^ (key & 7)) << 4)), vv);
-                const float p = pt[key];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vv[i], acc[i]);
-            }
-            if (g == 0) {
-                float vv[8];
-                unpack8(*reinterpret_cast<const uint4*>(sVT + (c << 4)), vv);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(p256, vv[i], acc[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-                acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-            }
-            if (g == 0) {
-                const float inv = 1.0f / sum;
-                uint4 w;
-                w.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-                w.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-                w.z = pack_bf16(acc[4] * inv, acc[5] * inv);
-                w.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-                *reinterpret_cast<uint4*>(out + (static_cast<size_t>(f) * kS + 256) * 1024 + head * 64 + c * 8) = w;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tv_done);
         }
     }
 
@@ -474,10 +546,12 @@ int make_qkv_hm_tmap(CUtensorMap* out, const void* qkv_hm, int n_rows, int box_r
 static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cudaStream_t s, long long* trace) {
     using namespace attn;
     const int n_items = n_frames * HVLM_VIT_HEADS;
-    CUtensorMap tq, tt;
+    CUtensorMap tq, tt16, tt1;
     int rc = make_qkv_hm_tmap(&tq, qkv_hm, n_frames * kS, 128);
     if (rc) return rc;
-    rc = make_qkv_hm_tmap(&tt, qkv_hm, n_frames * kS, 1);
+    rc = make_qkv_hm_tmap(&tt16, qkv_hm, n_frames * kS, 16);    // rows past the buffer are zero-filled by TMA
+    if (rc) return rc;
+    rc = make_qkv_hm_tmap(&tt1, qkv_hm, n_frames * kS, 1);
     if (rc) return rc;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -489,7 +563,7 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
     }
     const int max_ctas = 2 * num_sms();
     const int grid = n_items < max_ctas ? n_items : max_ctas;
-    if (launch_pdl(attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt, static_cast<__nv_bfloat16*>(out), n_items,
+    if (launch_pdl(attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1, static_cast<__nv_bfloat16*>(out), n_items,
                    trace) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
@@ -511,7 +585,7 @@ extern "C" int hvlm_vit_attention(const void* qkv_hm, void* out, int n_frames, v
     return launch_attention(qkv_hm, out, n_frames, static_cast<cudaStream_t>(stream));
 }
 
-// debug only (not part of the ABI header): trace[grid][2 roles][4 items][16 slots] clock64 timestamps
+// debug only (not part of the ABI header): trace[grid][5 warps][4 items][16 slots] clock64 timestamps
 extern "C" __attribute__((visibility("default"))) int hvlm_debug_attention_trace(const void* qkv_hm, void* out,
                                                                                  int n_frames, long long* trace,
                                                                                  void* stream, int) {

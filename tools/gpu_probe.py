@@ -244,7 +244,7 @@ def stage_attn_trace():
     qb[:16] *= 0.3
     out = torch.empty(Fb * 257, 1024, dtype=torch.bfloat16, device=dev)
     grid = min(Fb * 16, 2 * 148)
-    trace = torch.zeros(grid, 2, 4, 16, dtype=torch.int64, device=dev)
+    trace = torch.zeros(grid, 5, 4, 16, dtype=torch.int64, device=dev)
     fn = lib.hvlm_debug_attention_trace
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int]
@@ -258,9 +258,16 @@ def stage_attn_trace():
                "T1 o_read ok", "T1 S issued(+qk next)", "T1 p_full", "T1 PV issued", "", "", "v free"]
     names_s = ["item start", "qk_full", "T0 wait s", "T0 s_full", "T0 pass1 done", "T0 p arrived", "T0 o_full", "T0 o read",
                "T0 epi done", "T1 wait s", "T1 s_full", "T1 pass1 done", "T1 p arrived", "T1 o_full", "T1 o read", "T1 epi done"]
-    for cta in (0, 1, 150, 295):
-        for role, names in ((0, names_m), (1, names_s)):
-            for it in (1, 2):
+    # absolute time of each softmax warp's p arrival (relative to warp 1's item start): shows stragglers
+    for cta in (0, 1, 150):
+        for it in (1, 2):
+            b0 = int(t[cta, 1, it][0])
+            print(f"cta{cta} item{it} p-arrive T0/T1 per warp:",
+                  [(int(t[cta, w, it][5]) - b0, int(t[cta, w, it][12]) - b0) for w in (1, 2, 3, 4)],
+                  "epi done:", [(int(t[cta, w, it][8]) - b0, int(t[cta, w, it][15]) - b0) for w in (1, 2, 3, 4)], flush=True)
+    for cta in (0, 150):
+        for role, names in ((0, names_m), (1, names_s), (2, names_s), (3, names_s), (4, names_s)):
+            for it in (1,):
                 row = t[cta, role, it]
                 base = int(t[cta, role, it][0])
                 prev = base
@@ -270,7 +277,7 @@ def stage_attn_trace():
                     if nm and v:
                         line.append(f"{nm}:+{v - prev}")
                         prev = v
-                print(f"cta{cta} {'MMA' if role == 0 else 'SMX'} item{it} total={prev - base}: " + " | ".join(line), flush=True)
+                print(f"cta{cta} {'MMA' if role == 0 else 'SMX%d' % role} item{it} total={prev - base}: " + " | ".join(line), flush=True)
 
 
 def stage_gemm_epi():
