@@ -205,11 +205,12 @@ def stage_vit():
 
 def stage_bench():
     from hvlm_b200.tower import CLIPVisionTower
+    NF = int(os.environ.get("PROBE_FRAMES", "100"))
     sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=23)
     tower = CLIPVisionTower("synthetic", None, delay_load=True)
     tower.load_model(sd)
     tower = tower.to(dev)
-    px = torch.randn(100, 3, 224, 224, device=dev, dtype=torch.bfloat16)
+    px = torch.randn(NF, 3, 224, 224, device=dev, dtype=torch.bfloat16)
     for _ in range(2):
         tower.forward_hidden(px)
     torch.cuda.synchronize()
@@ -220,15 +221,15 @@ def stage_bench():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    RES["time_vit_100f"] = dict(ms=ms, frames_per_s=100 / ms * 1e3, tflops=100 * 155.29 / ms)
-    print(f"ViT 100 frames: {ms:.2f} ms  {100/ms*1e3:.0f} frames/s  {100*155.29/ms:.0f} TF/s", flush=True)
+    RES["time_vit_%df" % NF] = dict(ms=ms, frames_per_s=NF / ms * 1e3, tflops=NF * 155.29 / ms)
+    print(f"ViT {NF} frames: {ms:.3f} ms  {NF/ms*1e3:.0f} frames/s  {NF*155.29/ms:.0f} TF/s", flush=True)
     ops.profile_enable(True)
     for _ in range(3):
         tower.forward_hidden(px)
     prof = ops.profile_collect()
     ops.profile_enable(False)
-    flops = dict(qkv_gemm=2 * 25700 * 3072 * 1024, outproj_gemm=2 * 25700 * 1024 * 1024, fc1_gemm=2 * 25700 * 4096 * 1024,
-                 fc2_gemm=2 * 25700 * 4096 * 1024, attention=1600 * 4 * 257 * 257 * 64)
+    flops = dict(qkv_gemm=2 * NF * 257 * 3072 * 1024, outproj_gemm=2 * NF * 257 * 1024 * 1024, fc1_gemm=2 * NF * 257 * 4096 * 1024,
+                 fc2_gemm=2 * NF * 257 * 4096 * 1024, attention=NF * 16 * 4 * 257 * 257 * 64)
     for k, (t, n) in prof.items():
         extra = f"  {flops[k] / (t / n) / 1e9:7.0f} TF/s" if k in flops else ""
         print(f"  {k:14s} {t / 3:8.3f} ms/fwd  n={n // 3:3d}  avg {t / n * 1e3:7.1f} us{extra}", flush=True)
