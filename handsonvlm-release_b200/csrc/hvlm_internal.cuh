@@ -63,8 +63,14 @@ struct StageTimer {
 // Programmatic dependent launch (PDL): the kernel may be scheduled while its predecessor on the stream drains; it
 // runs its prologue (barrier init, TMEM alloc, descriptor prefetch) and then blocks in pdl_wait() until the
 // predecessor has completed and flushed.  Every kernel launched through this helper MUST call pdl_wait() before
-// touching global memory.  Opt-in with HVLM_PDL=1 (it measured slightly slower than plain stream order, see profile.cu).
+// touching global memory.  On for small batches, off for large ones, HVLM_PDL=1/0 overrides (policy and numbers in profile.cu).
 bool pdl_enabled();
+// RAII hint for the launches issued by the current host thread while it is alive (see profile.cu)
+struct PdlScope {
+    explicit PdlScope(bool on);
+    ~PdlScope();
+    int prev_;
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg{};

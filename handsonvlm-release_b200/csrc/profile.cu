@@ -19,15 +19,20 @@ struct Rec {
 static std::vector<Rec> g_recs;
 static std::vector<cudaEvent_t> g_free;
 
+// Programmatic dependent launch policy.  Measured on B200: for the 100-frame clip overlapping the ~3 us kernel prologues
+// does not pay (15.35 ms with PDL vs 15.20 ms without, same box), but for small batches the launch gaps and prologues are
+// a large share of every kernel: tower forward 1.91 -> 1.58 ms at 1 frame, 2.88 -> 2.53 ms at 10, 4.04 -> 3.76 ms at 20.
+// HVLM_PDL=1 / 0 forces it on / off; otherwise the caller's hint decides (vit_l14_fwd sets it for <= 32 frames).
+static thread_local int g_pdl_hint = 0;
 bool pdl_enabled() {
-    static const bool on = []() {
-        // measured on B200: overlapping the ~3 us kernel prologues does not pay (15.35 ms with PDL vs 15.20 ms
-        // without, same box), so programmatic dependent launch stays opt-in
+    static const int forced = []() {
         const char* e = getenv("HVLM_PDL");
-        return e && e[0] == '1';
+        return !e ? -1 : (e[0] == '1' ? 1 : 0);
     }();
-    return on;
+    return forced >= 0 ? forced == 1 : g_pdl_hint != 0;
 }
+PdlScope::PdlScope(bool on) : prev_(g_pdl_hint) { g_pdl_hint = on ? 1 : 0; }
+PdlScope::~PdlScope() { g_pdl_hint = prev_; }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

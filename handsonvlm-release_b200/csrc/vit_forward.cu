@@ -111,6 +111,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         return HVLM_ERR_ALIGN;
     const VitWorkspace ws = vit_workspace(n_frames);
     if (workspace_bytes < ws.total) return HVLM_ERR_WORKSPACE;
+    const PdlScope pdl(n_frames <= 32);      // small batches: overlap each kernel's prologue with its predecessor's tail
     hvlm_vit_layout L;
     int rc = hvlm_vit_l14_layout(n_layers_run, &L);
     if (rc) return rc;
