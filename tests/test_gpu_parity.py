@@ -378,8 +378,10 @@ def test_splice_backward_matches_oracle():
 # ------------------------------------------------------------------ ViT stages
 def test_qkv_and_attention_stage():
     """QKV GEMM with the column-block-major epilogue (3-D TMA stores) + attention (tensor-core
-    256x256 block, CUDA-core 257th key / query) against fp32 torch."""
-    for F in (1, 3, 7):
+    256x256 block, token-256 scores from the N=16 MMAs, 257th query row on CUDA cores) against fp32 torch.
+    F = 20 / 40 give 320 / 640 (frame, head) items on 296 persistent CTAs: the multi-item path (next item's loads,
+    token-256 blocks and first S tile issued behind the current item) is exercised with ragged item counts per CTA."""
+    for F in (1, 3, 7, 20, 40):
         y = synth.gen("attn.y", (F * 257, 1024), 1.0, F).to(torch.bfloat16)
         w = synth.gen("attn.w", (3072, 1024), 1024 ** -0.5, 1).to(torch.bfloat16)
         b = synth.gen("attn.b", (3072,), 0.1, 1)
