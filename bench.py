@@ -412,9 +412,10 @@ def run_ours(args):
             "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init ViT-L/14 + projector + embedding table, randn pixels)",
-            "config": {"workload": "configs[1]: HandsOnVLM-7B clip, %d clip(s)/GPU x 100 frames 224x224 -> CLIP ViT-L/14 "
+            "config": {"workload": "%s, %d clip(s)/GPU x 100 frames 224x224 -> CLIP ViT-L/14 "
                                    "(23 layers) -> LITA slow-fast pool (356 tokens) -> projector 1024->%d -> splice "
-                                   "(T=62 -> 417) + <hand_traj> gather" % (B, D),
+                                   "(T=62 -> 417) + <hand_traj> gather"
+                                   % ("configs[2]: HandsOnVLM-13B shapes" if D == 5120 else "configs[1]: HandsOnVLM-7B clip", B, D),
                        "clips_per_gpu": B, "frames_per_clip": FRAMES, "hidden": D, "parallelism": f"clip-sharded dp{world}",
                        "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": round(e2e_value, 1), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
