@@ -214,13 +214,17 @@ def stage_bench():
     for _ in range(2):
         tower.forward_hidden(px)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        tower.forward_hidden(px)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    reps = []
+    for _ in range(5):                      # 5 repeats of 10 forwards: report the median repeat (run-to-run noise ~2 %)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            tower.forward_hidden(px)
+        e1.record()
+        torch.cuda.synchronize()
+        reps.append(e0.elapsed_time(e1) / 10)
+    ms = sorted(reps)[len(reps) // 2]
+    print("  repeats (ms):", " ".join(f"{r:.3f}" for r in reps), flush=True)
     RES["time_vit_%df" % NF] = dict(ms=ms, frames_per_s=NF / ms * 1e3, tflops=NF * 155.29 / ms)
     print(f"ViT {NF} frames: {ms:.3f} ms  {NF/ms*1e3:.0f} frames/s  {NF*155.29/ms:.0f} TF/s", flush=True)
     ops.profile_enable(True)
