@@ -101,21 +101,48 @@ __device__ __forceinline__ void max_chunk32(const uint32_t (&v)[32], float& m) {
     }
     m = fmaxf(a, b);
 }
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes of work).  The softmax warps are
+// issue-bound as much as MUFU-bound (two of them share a scheduler), so fewer instructions per element is what pays.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // p = 2^(s*log2e - mxl) for one 32-column chunk; packed bf16 pairs; returns the chunk's sum
 __device__ __forceinline__ float exp_chunk32(const uint32_t (&v)[32], float log2e, float mxl, uint32_t (&pk)[16]) {
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+    const float nm = -mxl;
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), log2e, -mxl));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), log2e, -mxl));
-        const float p2 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 2]), log2e, -mxl));
-        const float p3 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 3]), log2e, -mxl));
-        s0 += p0 + p1;
-        s1 += p2 + p3;
+        float x0, x1, x2, x3;
+        ffma2(x0, x1, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), log2e, log2e, nm, nm);
+        ffma2(x2, x3, __uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3]), log2e, log2e, nm, nm);
+        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+        fadd2(s0, s1, s0, s1, p0, p1);
+        fadd2(t0, t1, t0, t1, p2, p3);
         pk[j] = pack_bf16(p0, p1);
         pk[j + 1] = pack_bf16(p2, p3);
     }
-    return s0 + s1;
+    return (s0 + s1) + (t0 + t1);
 }
 
 // debug: per-phase timestamps (trace == nullptr in production)
@@ -497,7 +524,10 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                     const uint32_t* o = j < 4 ? &o0[8 * j] : &o1[8 * (j - 4)];
                     float y[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = fmaf(p_tail, vt[i], __uint_as_float(o[i])) * inv_sum;
+                    for (int i = 0; i < 8; i += 2) {
+                        ffma2(y[i], y[i + 1], p_tail, p_tail, vt[i], vt[i + 1], __uint_as_float(o[i]), __uint_as_float(o[i + 1]));
+                        fmul2(y[i], y[i + 1], y[i], y[i + 1], inv_sum, inv_sum);
+                    }
                     rowv[j].x = pack_bf16(y[0], y[1]);
                     rowv[j].y = pack_bf16(y[2], y[3]);
                     rowv[j].z = pack_bf16(y[4], y[5]);
