@@ -101,32 +101,8 @@ __device__ __forceinline__ void max_chunk32(const uint32_t (&v)[32], float& m) {
     }
     m = fmaxf(a, b);
 }
-// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes of work).  The softmax warps are
-// issue-bound as much as MUFU-bound (two of them share a scheduler), so fewer instructions per element is what pays.
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1)
-        : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1)
-        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t}"
-        : "=f"(d0), "=f"(d1)
-        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
+// The softmax warps are issue-bound as much as MUFU-bound (two of them share a scheduler), so the exp pass and the
+// epilogue use the packed fp32x2 FMA / ADD / MUL of hvlm_ptx.cuh: fewer instructions per element is what pays.
 // p = 2^(s*log2e - mxl) for one 32-column chunk; packed bf16 pairs; returns the chunk's sum
 __device__ __forceinline__ float exp_chunk32(const uint32_t (&v)[32], float log2e, float mxl, uint32_t (&pk)[16]) {
     float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
