@@ -18,6 +18,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "hvlm_b200.h")
 F32, BF16, F16 = 0, 1, 2
 POOL_MODES = {"temporal_spatial_pool": 0, "spatial_pool": 1, "temporal": 2, "spatial": 3, "temporal_spatial": 4}
 SPLICE_LLAVA, SPLICE_HANDSONVLM = 0, 1
+SPLICE_FLAG_IM_START_END = 0x100   # OR-able into the splice variant (include/hvlm_b200.h)
 EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PLAN_ERR_LEN_OVERFLOW, PLAN_ERR_IMG_OVERFLOW, PLAN_ERR_HAND_COUNT, PLAN_ERR_BAD_ID, PLAN_NOT_UNIFORM = 1, 2, 4, 8, 16
 VIT_MAX_LAYERS = 24

@@ -219,8 +219,9 @@ def _raise_on_status(bits: int):
 
 
 def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual, visual_mask=None,
-                  future_hands=None, is_evaluate: bool = False):
-    """Core of both prepare_inputs_labels_for_multimodal variants -> (attention_mask', embeds, labels')."""
+                  future_hands=None, is_evaluate: bool = False, im_start_end: bool = False):
+    """Core of both prepare_inputs_labels_for_multimodal variants -> (attention_mask', embeds, labels').
+    ``im_start_end``: the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch of llava_arch.py:146-161,172-181."""
     table = host.get_model().embed_tokens.weight
     B, T = input_ids.shape
     n_img, Nv, D = visual.shape
@@ -252,7 +253,7 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
         host._hvlm_splice_status = status                             # device flag; check lazily if wanted
     embeds, new_labels, new_mask = ops.splice_gather(
         src_index, hand_code, lens_d, hand_scale, input_ids, labels, attention_mask, table, visual, visual_mask,
-        future_hands if hand_mode else None, variant)
+        future_hands if hand_mode else None, variant | (L.SPLICE_FLAG_IM_START_END if im_start_end else 0))
     if labels is None:
         new_labels = None
     if attention_mask is None:
@@ -301,22 +302,21 @@ class LlavaMetaForCausalLM(ABC):
         return self.images_to_tokens(images)
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images):
-        """llava_arch.py:110-234 (released flags: no <im_start>/<im_end>)."""
+        """llava_arch.py:110-234, including the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch (:146-161)."""
         vision_tower = self.get_vision_tower()
         if vision_tower is None or images is None or input_ids.shape[1] == 1:
             if past_key_values is not None and vision_tower is not None and images is not None and input_ids.shape[1] == 1:
                 attention_mask = torch.ones((attention_mask.shape[0], past_key_values[-1][-1].shape[-2] + 1),
                                             dtype=attention_mask.dtype, device=attention_mask.device)
             return input_ids, attention_mask, past_key_values, None, labels
-        if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
-            raise NotImplementedError("mm_use_im_start_end splice variant is not part of the released config")
+        ise = bool(getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False))
         image_features = self.visual_to_tokens(images)
         if isinstance(image_features, (list, tuple)):
             if any(x.shape != image_features[0].shape for x in image_features):
                 raise NotImplementedError("per-image variable token counts are not supported by the splice kernel")
             image_features = torch.stack(list(image_features), 0)
         new_mask, embeds, new_labels = splice_tokens(self, L.SPLICE_LLAVA, input_ids, attention_mask, labels,
-                                                     image_features)
+                                                     image_features, im_start_end=ise)
         return None, new_mask, past_key_values, embeds, new_labels
 
 

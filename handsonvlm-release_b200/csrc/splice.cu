@@ -165,7 +165,12 @@ splice_fwd_kernel(const int32_t* __restrict__ src_index, const int8_t* __restric
     if (code >= 0) {
         const int64_t ipos = static_cast<int64_t>(b) * Tlen + code;
         src = table + ids[ipos] * D;
-        if (labels) lab = labels[ipos];
+        if (labels) {
+            // <im_end> right after an image token keeps the image-token position's label in the im_start_end branch
+            const bool after_img = (variant & HVLM_SPLICE_FLAG_IM_START_END) && code > 0 &&
+                                   ids[ipos - 1] == HVLM_IMAGE_TOKEN_INDEX;
+            lab = labels[after_img ? ipos - 1 : ipos];
+        }
         if (mask) mk = mask[ipos];
     } else if (code != kPad) {
         const int g = -(code + 1);
@@ -175,7 +180,7 @@ splice_fwd_kernel(const int32_t* __restrict__ src_index, const int8_t* __restric
     if (threadIdx.x == 0) {
         if (out_labels) out_labels[orow] = lab;
         if (out_mask) {
-            if (variant == HVLM_SPLICE_LLAVA && mask) {
+            if ((variant & 0xff) == HVLM_SPLICE_LLAVA && mask) {
                 // llava_arch.py:215-232: True x (len - T) prepended, original mask, False right-pad
                 const int len = lens[b];
                 const int lead = len - Tlen;
@@ -249,7 +254,8 @@ extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B
     using namespace hvlm;
     if (!ids || !counts || !src_index || !hand_code || !lens || !status) return HVLM_ERR_BAD_ARG;
     if (B <= 0 || T <= 0 || Nv <= 0 || n_img <= 0 || L <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
-    if (variant != HVLM_SPLICE_LLAVA && variant != HVLM_SPLICE_HANDSONVLM) return HVLM_ERR_BAD_ARG;
+    if ((variant & 0xff) != HVLM_SPLICE_LLAVA && (variant & 0xff) != HVLM_SPLICE_HANDSONVLM) return HVLM_ERR_BAD_ARG;
+    variant &= 0xff;        // the plan does not depend on the flags
     if (hand_mode < 0 || hand_mode > 2 || n_hand_points < 0 || n_hand_points > 127) return HVLM_ERR_BAD_ARG;
     StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_plan_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(

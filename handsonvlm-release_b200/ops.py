@@ -448,8 +448,9 @@ def _(d_embeds, src_index, ids, n_visual_rows, vocab, need_table):
 
 
 def _splice_setup(ctx, inputs, output):
-    src_index, _, _, _, ids, _, _, table, visual, _, _, _ = inputs
+    src_index, _, _, _, ids, _, _, table, visual, _, _, variant = inputs
     ctx.save_for_backward(src_index, ids)
+    ctx.im_start_end = bool(variant & L.SPLICE_FLAG_IM_START_END)
     ctx.vshape = visual.shape
     ctx.vocab = table.shape[0]
     ctx.need_table = table.requires_grad
@@ -463,6 +464,16 @@ def _splice_backward(ctx, d_embeds, d_labels, d_mask):
     gv = gt = None
     if d_embeds is not None and (ctx.need_table or ctx.need_visual):
         n_img, Nv, D = ctx.vshape
+        if ctx.im_start_end and ctx.need_table:
+            # llava_arch.py:150,181: every text segment is .detach()ed except the token right before / after an image
+            # token -> drop the other text rows from the plan the backward kernel walks (INT32_MIN = skip)
+            img = ids == -200
+            near = torch.zeros_like(img)
+            near[:, :-1] |= img[:, 1:]
+            near[:, 1:] |= img[:, :-1]
+            is_text = src_index >= 0
+            keep = near.gather(1, src_index.clamp_min(0).long())
+            src_index = torch.where(is_text & ~keep, torch.full_like(src_index, -2 ** 31), src_index)
         d_visual, d_table = splice_bwd(d_embeds, src_index, ids, n_img * Nv, ctx.vocab, ctx.need_table)
         if ctx.need_visual:
             gv = d_visual.reshape(n_img, Nv, D).to(ctx.vdtype)

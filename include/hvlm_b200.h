@@ -197,6 +197,10 @@ HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok
  * L is chosen by the caller: T-1+Nv when every sample has exactly one image token (the collator's
  * contract, hybrid_dataset.py:155-158), else max(lens) after reading `lens` back.
  * ---------------------------------------------------------------------------------------------- */
+/* OR-able into `variant` of hvlm_splice_plan / hvlm_splice_fwd: the `tune_mm_mlp_adapter && mm_use_im_start_end` branch of
+ * llava_arch.py:146-161,172-173 -- the embeddings are the same rows, but the token right after an image token (<im_end>)
+ * takes the label of the image-token position (`cur_labels[image_token_start:image_token_start+1]`, :159). */
+#define HVLM_SPLICE_FLAG_IM_START_END 0x100
 #define HVLM_IGNORE_INDEX (-100)
 #define HVLM_IMAGE_TOKEN_INDEX (-200)
 #define HVLM_HAND_TRAJ_TOKEN_ID 32100

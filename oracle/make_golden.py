@@ -236,6 +236,31 @@ def golden_splice(ns):
     save("splice_llava_t1", mask=m2, embeds_is_none=e2 is None, ids=r_ids)
 
 
+def golden_splice_im_start_end(ns):
+    """The ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch of llava_arch.py:146-161,172-181, run as is: outputs and
+    the gradient that reaches ``embed_tokens.weight`` (only the two tokens around the image token are not detached)."""
+    sd, proj, emb = small_parts()
+    tower = ref_shim.build_tower(ns, hf_model(SMALL, sd), select_layer=-2)
+    LV = ns.llava_arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal
+    cfg = types.SimpleNamespace(input_type="image", tune_mm_mlp_adapter=True, mm_use_im_start_end=True)
+    ids, mask, _ = synth.prompt_llava(seed=33)
+    ids = torch.cat([ids, ids], 0).clone()
+    ids[1, 20:30] = torch.arange(100, 110)
+    labels = torch.arange(ids.numel(), dtype=torch.int64).reshape(ids.shape) + 1000      # all distinct
+    mask = torch.ones_like(ids, dtype=torch.bool)
+    host = make_host(ns, ns.lita_arch.LitaMetaForCausalLM, tower, proj, emb, cfg, ids.shape[0])
+    emb.weight.grad = None
+    with torch.enable_grad():
+        r_ids, m2, _, e2, l2 = LV(host, ids, mask, None, labels, synth.pixels((2, 3, 224, 224), seed=16))
+        w = synth.gen("ise.dout", tuple(e2.shape), 1.0, seed=16)
+        (e2 * w).sum().backward()
+    g = emb.weight.grad
+    rows = torch.nonzero(g.abs().sum(1) > 0).flatten()
+    save("splice_llava_im_start_end", ids=ids, in_mask=mask, in_labels=labels, mask=m2, embeds=e2.detach(), labels=l2,
+         grad_rows=rows, grad_vals=g[rows])
+    emb.weight.grad = None
+
+
 def golden_gather(ns):
     """Execute the reference's inline gather (handsonvlm.py, inside forward) from its source text."""
     import inspect
@@ -314,6 +339,7 @@ def main():
     golden_traj(ns)
     golden_lita(ns)
     golden_splice(ns)
+    golden_splice_im_start_end(ns)
     golden_vit_full(ns)
 
 

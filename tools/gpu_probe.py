@@ -390,6 +390,49 @@ def stage_traj():
                   f"with host launch", flush=True)
 
 
+def stage_twostream():
+    """Two half-batches on two streams: does one half's LayerNorm / kernel tails hide under the other half's GEMMs?"""
+    import types as _t
+    from hvlm_b200.tower import CLIPVisionTower
+    sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=23)
+    tw = CLIPVisionTower("synthetic", _t.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    tw.load_model(sd)
+    tw = tw.to(dev)
+    px = torch.randn(100, 3, 224, 224, device=dev, dtype=torch.bfloat16)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+
+    def run(parts):
+        if parts == 1:
+            return [tw.forward_hidden(px)]
+        cur = torch.cuda.current_stream()
+        outs = []
+        chunks = px.chunk(parts)
+        for st, c in zip(streams, chunks):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(tw.forward_hidden(c))
+        for st in streams[:parts]:
+            cur.wait_stream(st)
+        return outs
+
+    ref = run(1)[0]
+    for parts in (1, 2, 1, 2, 4):
+        for _ in range(3):
+            o = run(parts)
+        torch.cuda.synchronize()
+        reps = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                o = run(parts)
+            e1.record()
+            torch.cuda.synchronize()
+            reps.append(e0.elapsed_time(e1) / 10)
+        same = torch.equal(torch.cat(o), ref)
+        print(f"parts={parts}: median {sorted(reps)[2]:.3f} ms  ({' '.join(f'{r:.2f}' for r in reps)})  bit-identical={same}", flush=True)
+
+
 def stage_latency():
     """Small-batch tower latency (configs[0]: one image): stream launches vs one CUDA-graph replay."""
     import types as _t
