@@ -374,7 +374,12 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
         visual_tokens, visual_mask = helper.pipeline(images=images, **kwargs)
         assert visual_tokens.shape == torch.Size([self.B, visual_tokens.shape[1], self.token_dim]), visual_tokens.shape
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
-            raise NotImplementedError("mm_use_im_start_end splice variant is not part of the released config")
+            # handsonvlm.py:263-286,343-344: <im_start>/<im_end> branch -- no hand embeddings on the tail, the <im_end>
+            # slot takes the image position's label and mask entry, last_visual_token_index is left untouched
+            new_mask, embeds, new_labels = splice_tokens(
+                self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None, None, True,
+                im_start_end=True)
+            return None, new_mask, past_key_values, embeds, new_labels
         new_mask, embeds, new_labels = splice_tokens(
             self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None,
             kwargs.get("future_hands"), kwargs.get("is_evaluate", False))

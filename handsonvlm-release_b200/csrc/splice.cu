@@ -165,13 +165,12 @@ splice_fwd_kernel(const int32_t* __restrict__ src_index, const int8_t* __restric
     if (code >= 0) {
         const int64_t ipos = static_cast<int64_t>(b) * Tlen + code;
         src = table + ids[ipos] * D;
-        if (labels) {
-            // <im_end> right after an image token keeps the image-token position's label in the im_start_end branch
-            const bool after_img = (variant & HVLM_SPLICE_FLAG_IM_START_END) && code > 0 &&
-                                   ids[ipos - 1] == HVLM_IMAGE_TOKEN_INDEX;
-            lab = labels[after_img ? ipos - 1 : ipos];
-        }
-        if (mask) mk = mask[ipos];
+        // <im_end> right after an image token keeps the image-token position's label (and, in the HandsOnVLM splice,
+        // its attention-mask entry) in the im_start_end branch: llava_arch.py:159, handsonvlm.py:278,283
+        const bool after_img = (variant & HVLM_SPLICE_FLAG_IM_START_END) && code > 0 &&
+                               ids[ipos - 1] == HVLM_IMAGE_TOKEN_INDEX;
+        if (labels) lab = labels[after_img ? ipos - 1 : ipos];
+        if (mask) mk = mask[after_img ? ipos - 1 : ipos];
     } else if (code != kPad) {
         const int g = -(code + 1);
         src = visual + static_cast<int64_t>(g) * D;

@@ -199,7 +199,9 @@ HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok
  * ---------------------------------------------------------------------------------------------- */
 /* OR-able into `variant` of hvlm_splice_plan / hvlm_splice_fwd: the `tune_mm_mlp_adapter && mm_use_im_start_end` branch of
  * llava_arch.py:146-161,172-173 -- the embeddings are the same rows, but the token right after an image token (<im_end>)
- * takes the label of the image-token position (`cur_labels[image_token_start:image_token_start+1]`, :159). */
+ * takes the label of the image-token position (`cur_labels[image_token_start:image_token_start+1]`, :159); in the
+ * HandsOnVLM splice (handsonvlm.py:263-286) the position-spliced attention mask follows the same rule (:283) and the
+ * caller passes hand_mode 0 (that branch adds no hand embeddings, :343-344). */
 #define HVLM_SPLICE_FLAG_IM_START_END 0x100
 #define HVLM_IGNORE_INDEX (-100)
 #define HVLM_IMAGE_TOKEN_INDEX (-200)

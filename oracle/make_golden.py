@@ -261,6 +261,27 @@ def golden_splice_im_start_end(ns):
     emb.weight.grad = None
 
 
+def golden_splice_hvlm_im_start_end(ns):
+    """HandsOnVLM's own splice with tune_mm_mlp_adapter + mm_use_im_start_end (handsonvlm.py:263-286,343-344)."""
+    sd, proj, emb = small_parts()
+    tower = ref_shim.build_tower(ns, hf_model(SMALL, sd), select_layer=-2)
+    HV = ns.handsonvlm.HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal
+    t = 4
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=2, seed=23, n_pre=7, n_post=5)
+    labels = torch.arange(ids.numel(), dtype=torch.int64).reshape(ids.shape) + 1000
+    mask = torch.ones_like(ids, dtype=torch.bool)
+    s = int((ids[0] == synth.IMAGE_TOKEN_INDEX).nonzero()[0])
+    mask[0, s] = False                  # visible in the output only through the <im_end> slot rule
+    mask[1, -2:] = False
+    host = _hvlm_host(ns, tower, proj, emb, 2)
+    host.config.tune_mm_mlp_adapter = True
+    host.config.mm_use_im_start_end = True
+    px = synth.pixels((2, t, 3, 224, 224), seed=17)
+    _, m2, _, e2, l2 = HV(host, ids, mask, None, labels, px, is_evaluate=False, future_hands=fh, future_valid=fv)
+    save("splice_hvlm_im_start_end", ids=ids, in_mask=mask, in_labels=labels, mask=m2, mask_dtype=str(m2.dtype),
+         embeds=e2.detach(), labels=l2, t=t, has_last_visual_token_index=hasattr(host, "last_visual_token_index"))
+
+
 def golden_gather(ns):
     """Execute the reference's inline gather (handsonvlm.py, inside forward) from its source text."""
     import inspect
@@ -340,6 +361,7 @@ def main():
     golden_lita(ns)
     golden_splice(ns)
     golden_splice_im_start_end(ns)
+    golden_splice_hvlm_im_start_end(ns)
     golden_vit_full(ns)
 
 

@@ -215,7 +215,7 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
     variant 'handsonvlm' -- ``HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal``
                             (handsonvlm/model/language_model/handsonvlm.py:212-451)
 
-    im_start_end (variant 'llava' only) -- the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch
+    im_start_end         -- the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch
                             (llava_arch.py:146-161,172-173,180-181): same embedding rows; the token right after an
                             image token takes the label of the image-token position (:159); text embeddings other than
                             the two tokens around an image are detached (see ``splice_backward``).
@@ -238,11 +238,12 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
         for r, (kind, idx) in enumerate(plan):
             if kind == 0:
                 e[r] = embed_w[ids[b, idx]]
+                after_img = im_start_end and idx > 0 and int(ids[b, idx - 1]) == IMAGE_TOKEN_INDEX
                 if lab is not None:
-                    after_img = im_start_end and idx > 0 and int(ids[b, idx - 1]) == IMAGE_TOKEN_INDEX
                     lab[r] = labels[b, idx - 1 if after_img else idx]
                 if msk is not None:
-                    msk[r] = attention_mask[b, idx]
+                    # only the HandsOnVLM splice builds its mask by position (handsonvlm.py:283)
+                    msk[r] = attention_mask[b, idx - 1 if (after_img and variant == "handsonvlm") else idx]
             else:
                 img = slot + idx // Nv
                 e[r] = visual[img, idx % Nv]
@@ -250,7 +251,7 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
                     lab[r] = IGNORE_INDEX
                 if msk is not None:
                     msk[r] = True if visual_mask is None else visual_mask[img, idx % Nv]
-        if variant == "handsonvlm" and k_img > 0:
+        if variant == "handsonvlm" and k_img > 0 and not im_start_end:     # (:343-344: that branch adds nothing)
             # tail segment = text after the last image token (handsonvlm.py:342-396)
             last_img_pos = int(torch.where(ids[b] == IMAGE_TOKEN_INDEX)[0][-1])
             tail = ids[b, last_img_pos + 1:]

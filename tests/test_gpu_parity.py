@@ -371,6 +371,24 @@ def test_splice_llava_im_start_end_variant(golden, small):
     assert "mm_use_im_start_end" in arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal.__doc__
 
 
+def test_splice_hvlm_im_start_end_variant(golden, small):
+    """HandsOnVLM splice with tune_mm_mlp_adapter + mm_use_im_start_end (handsonvlm.py:263-286,343-344)."""
+    g = golden("splice_hvlm_im_start_end")
+    sd, proj, emb = small
+    vis = _small_visual(small, synth.pixels((2, int(g["t"]), 3, 224, 224), seed=17))
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=emb.weight.data.to(DEV))),
+        config=types.SimpleNamespace(hvlm_static_splice=False))
+    m2, e2, l2 = arch.splice_tokens(host, L.SPLICE_HANDSONVLM, T(g["ids"]).to(DEV), T(g["in_mask"]).to(DEV),
+                                    T(g["in_labels"]).to(DEV), vis.to(DEV), None, None, True, im_start_end=True)
+    assert torch.equal(l2.cpu(), T(g["labels"]))
+    assert m2.dtype == torch.bool and torch.equal(m2.cpu(), T(g["mask"]))
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    ro = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, emb.weight.data, "handsonvlm",
+                        im_start_end=True)
+    assert torch.equal(e2.cpu(), ro[1])
+
+
 def test_splice_static_mode_no_sync_and_status_flag():
     D = 256
     table = synth.embed_table(D)

@@ -218,6 +218,19 @@ def test_splice_llava_im_start_end(golden, small):
     assert relmax(d_table[rows], T(g["grad_vals"])) <= 1e-6
 
 
+def test_splice_hvlm_im_start_end(golden, small):
+    """HandsOnVLM's own splice with both flags set (handsonvlm.py:263-286,343-344): position-spliced mask follows the
+    <im_end> rule too, and the tail gets no hand embeddings."""
+    g = golden("splice_hvlm_im_start_end")
+    _, _, _, ew = small
+    vis = small_visual(small, synth.pixels((2, int(g["t"]), 3, 224, 224), seed=17))
+    m2, e2, l2 = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), vis, ew, "handsonvlm",
+                                im_start_end=True)
+    assert torch.equal(l2, T(g["labels"])) and torch.equal(m2, T(g["mask"])) and m2.dtype == torch.bool
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    assert not bool(g["has_last_visual_token_index"])
+
+
 def test_splice_cfg1_shapes(golden):
     g = golden("splice_llava_cfg1")
     assert g["embeds"].shape == (1, 311, SMALL_D)
