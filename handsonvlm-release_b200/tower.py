@@ -19,6 +19,17 @@ _CFG = dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_
             patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5, projection_dim=768)
 
 
+def _load_clip_state_dict(src: str) -> dict:
+    import os
+    if os.path.isfile(src):
+        if src.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            return load_file(src)
+        return torch.load(src, map_location="cpu")
+    from transformers import CLIPVisionModel                      # directory or hub id, like the reference
+    return CLIPVisionModel.from_pretrained(src).state_dict()
+
+
 class CLIPVisionTower(nn.Module):
     def __init__(self, vision_tower="openai/clip-vit-large-patch14", args=None, delay_load=False):
         super().__init__()
@@ -34,13 +45,14 @@ class CLIPVisionTower(nn.Module):
 
     # -- loading -------------------------------------------------------------------------------
     def load_model(self, state_dict=None):
-        """``state_dict``: HF-named CLIPVisionModel tensors.  (The reference calls ``from_pretrained`` here;
-        there is no network in this environment, so the weights are handed in; a path to a ``.pt``/``.bin``
-        state dict is also accepted.)"""
+        """``state_dict``: HF-named CLIPVisionModel tensors, or where to find them.  With no argument this does what
+        the reference does (clip_encoder.py:22-26): ``CLIPVisionModel.from_pretrained(self.vision_tower_name)`` -- a
+        hub id (needs the HF cache or a network) or a local ``save_pretrained`` directory.  A path to a ``.pt`` /
+        ``.bin`` / ``.safetensors`` state dict is accepted as well."""
         if state_dict is None:
             state_dict = self.vision_tower_name
         if isinstance(state_dict, str):
-            state_dict = torch.load(state_dict, map_location="cpu")
+            state_dict = _load_clip_state_dict(state_dict)
         dev = self.weight_blob.device
         blob = pack_vit_weights(state_dict, n_layers=self.n_layers_needed)
         self._blob_layers = blob.hvlm_n_layers

@@ -491,6 +491,27 @@ def test_vit_l14_tracks_bf16_operand_oracle(tower23):
     assert relmax(hid, emu) <= 4e-3
 
 
+def test_tower_load_model_from_files(tower23, tmp_path):
+    """load_model accepts what the reference's from_pretrained accepts (a save_pretrained directory) and plain
+    state-dict files; the packed weight blob is identical to the one packed from the in-memory state dict."""
+    import transformers
+    tw, sd = tower23("hf")
+    f = tmp_path / "clip_sd.pt"
+    torch.save(sd, f)
+    t2 = CLIPVisionTower(str(f), types.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    t2.load_model()
+    assert t2.is_loaded and torch.equal(t2.weight_blob.cpu(), tw.weight_blob.cpu())
+    cfg = transformers.CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                                        num_attention_heads=16, image_size=224, patch_size=14, projection_dim=768)
+    hf = transformers.CLIPVisionModel(cfg)
+    hf.load_state_dict({k: v for k, v in sd.items()}, strict=False)
+    d = tmp_path / "hf_dir"
+    hf.save_pretrained(d)
+    t3 = CLIPVisionTower(str(d), types.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    t3.load_model()
+    assert torch.equal(t3.weight_blob.cpu(), tw.weight_blob.cpu())
+
+
 def test_tower_rejects_wrong_image_size(tower23):
     tw, _ = tower23("hf")
     with pytest.raises(ValueError):
