@@ -512,6 +512,27 @@ def test_tower_load_model_from_files(tower23, tmp_path):
     assert torch.equal(t3.weight_blob.cpu(), tw.weight_blob.cpu())
 
 
+@pytest.mark.parametrize("select_layer,select_feature", [(-1, "patch"), (-2, "cls_patch"), (12, "patch"), (0, "cls_patch")])
+def test_tower_select_layer_and_feature_variants(select_layer, select_feature):
+    """Every (select_layer, select_feature) the reference's feature_select accepts (clip_encoder.py:29-37): the full
+    24-layer tower (-1), CLS kept, a positive layer index, and index 0 = the pre-LayerNorm embeddings."""
+    sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=24)
+    args = types.SimpleNamespace(mm_vision_select_layer=select_layer, mm_vision_select_feature=select_feature)
+    tw = CLIPVisionTower("synthetic", args, delay_load=True)
+    tw.load_model(sd)
+    tw = tw.to(DEV)
+    px = synth.pixels((1, 3, 224, 224), seed=6)
+    feats = tw(px.to(DEV))
+    ref = restate.tower_forward(px, sd, select_layer, synth.VIT_L14, select_feature)
+    assert feats.shape == ref.shape == (1, 257 if select_feature == "cls_patch" else 256, 1024)
+    assert relmax(feats, ref) <= TOL_BF16
+    with pytest.raises(ValueError):
+        bad = CLIPVisionTower("synthetic", types.SimpleNamespace(mm_vision_select_layer=-2,
+                                                                 mm_vision_select_feature="cls"), delay_load=True)
+        bad.load_model(sd)
+        bad.to(DEV)(px.to(DEV))
+
+
 def test_tower_rejects_wrong_image_size(tower23):
     tw, _ = tower23("hf")
     with pytest.raises(ValueError):
