@@ -288,15 +288,19 @@ class LlavaMetaForCausalLM(ABC):
         return tok.reshape(feats.shape[0], feats.shape[1], -1)
 
     def images_to_tokens(self, images):
-        if type(images) is list or images.ndim == 5:
-            concat_images = torch.cat([image for image in images], dim=0)
-            image_features = self.encode_images(concat_images)
-            split_sizes = [image.shape[0] for image in images]
-            image_features = torch.split(image_features, split_sizes, dim=0)
-            image_features = [x.flatten(0, 1) for x in image_features]
-        else:
-            image_features = self.encode_images(images)
-        return image_features
+        """llava_arch.py:95-106.  A plain batch [N,3,H,W] -> [N,256,D].  A list (or a 5-d stack) of per-sample image
+        groups is encoded in ONE tower call and handed back as one flat [n_i*256, D] token block per sample."""
+        grouped = isinstance(images, (list, tuple)) or images.ndim == 5
+        if not grouped:
+            return self.encode_images(images)
+        groups = list(images)
+        feats = self.encode_images(torch.cat(groups, dim=0))                 # [sum n_i, 256, D]
+        out, start = [], 0
+        for g in groups:
+            n = g.shape[0]
+            out.append(feats[start:start + n].reshape(n * feats.shape[1], feats.shape[2]))
+            start += n
+        return out
 
     def visual_to_tokens(self, images):
         return self.images_to_tokens(images)
