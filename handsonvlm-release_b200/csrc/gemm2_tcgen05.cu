@@ -171,7 +171,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_bh, const __grid_constant__ CUtensorMap tma_c, int M, int N,
                      int K, EpiArgs ep, int split_tail) {
-    static_assert(epi_is_staged<EPI>(), "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
+    static_assert(epi_is_staged<EPI>() || EPI == EPI_PATCH, "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
     static_assert(!(LN && G == 2), "the fused-LayerNorm warps and the second epilogue group use the same warp slots");
     constexpr int kStages = Cfg2<G>::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -297,7 +297,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const int grp = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
-        constexpr bool kF32 = epi_out_f32<EPI>();
+        constexpr bool kF32 = epi_out_f32<EPI>() || EPI == EPI_PATCH;
         constexpr int kUnitCols = kF32 ? 32 : 64;
         constexpr int kUnits = BN / kUnitCols / G;          // units per group (whole tile)
         static_assert(kUnits >= 2, "half tiles need at least one unit per group");
@@ -366,6 +366,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     if (elect_one()) {
                         if constexpr (EPI == EPI_RESID_F32) {
                             tma_reduce_add_2d(&tma_c, buf, n0, m0);
+                        } else if constexpr (EPI == EPI_PATCH) {
+                            // hidden [frame][257][1024]: this CTA's 128 patch rows land behind the frame's CLS row
+                            tma_store_3d(&tma_c, buf, n0, 1 + (m0 & 255), m0 >> 8);
                         } else if constexpr (EPI == EPI_QKV_HM) {
                             tma_store_3d(&tma_c, buf, 0, m0, n0 >> 6);
                         } else {
@@ -470,7 +473,13 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         if (!ep.out || !aligned16(ep.out)) return HVLM_ERR_ALIGN;
         uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
         int rc;
-        if constexpr (EPI == EPI_QKV_HM) {
+        if constexpr (EPI == EPI_PATCH) {
+            if (N != 1024 || (M & 255) != 0) return HVLM_ERR_BAD_SHAPE;
+            uint64_t d3[3] = {1024, HVLM_VIT_TOKENS, static_cast<uint64_t>(M >> 8)};
+            uint64_t s3[2] = {1024 * 4, static_cast<uint64_t>(HVLM_VIT_TOKENS) * 1024 * 4};
+            uint32_t b3[3] = {32, BM, 1};
+            rc = make_tmap_f32(&tc, ep.out, 3, d3, s3, b3);
+        } else if constexpr (EPI == EPI_QKV_HM) {
             if (N != 3072) return HVLM_ERR_BAD_SHAPE;
             rc = make_qkv_hm_tmap(&tc, ep.out, M, BM);
         } else if constexpr (epi_out_f32<EPI>()) {
@@ -533,6 +542,7 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
         case EPI_BIAS_F32: return launch_two<EPI_BIAS_F32>(A, B, M, N, K, ep, s);
         case EPI_GELU_BF16: return launch_two<EPI_GELU_BF16>(A, B, M, N, K, ep, s);
         case EPI_GELU_F32: return launch_two<EPI_GELU_F32>(A, B, M, N, K, ep, s);
+        case EPI_PATCH: return launch_two<EPI_PATCH>(A, B, M, N, K, ep, s);
         case EPI_RESID_F32:
             if (ep.ln_out != nullptr) {
                 if (N != 1024 || !ep.ln_gamma || !ep.ln_beta || !ep.ln_count) return HVLM_ERR_BAD_ARG;

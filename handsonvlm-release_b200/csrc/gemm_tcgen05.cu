@@ -164,15 +164,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], int m,
     } else if constexpr (EPI == EPI_PATCH) {
         const int f = m >> 8;
         const int p = m & 255;
-        const float4* pos4 = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(1 + p) * N + n0);
         float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) +
                                               (static_cast<size_t>(f) * HVLM_VIT_TOKENS + 1 + p) * N + n0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float4 e = __ldg(pos4 + j);
-            o[j] = make_float4(__uint_as_float(acc[4 * j + 0]) + e.x, __uint_as_float(acc[4 * j + 1]) + e.y,
-                               __uint_as_float(acc[4 * j + 2]) + e.z, __uint_as_float(acc[4 * j + 3]) + e.w);
-        }
+        for (int j = 0; j < 8; ++j)
+            o[j] = make_float4(__uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]),
+                               __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
     }
 }
 

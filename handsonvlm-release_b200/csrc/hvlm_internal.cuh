@@ -18,7 +18,7 @@ enum Epi : int {
     EPI_GELU_BF16 = 2,   // out bf16 [M,N] = quick_gelu(acc + bias)
     EPI_RESID_F32 = 3,   // out f32  [M,N] += acc + bias  (TMA reduce-add into the residual stream, in place)
     EPI_QKV_HM = 4,      // ViT: bf16 q|k|v written column-block-major [48][M][64] (3-D TMA stores)
-    EPI_PATCH = 5,       // ViT: x0[f*257+1+p, n] = acc + pos[1+p, n]   (f32)
+    EPI_PATCH = 5,       // ViT: x0[f*257+1+p, n] = acc   (f32; the position embedding is added by the pre-LayerNorm)
     EPI_GELU_F32 = 6     // out f32 = quick_gelu(acc + bias)            (tests only)
 };
 

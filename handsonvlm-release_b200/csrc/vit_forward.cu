@@ -13,7 +13,7 @@
 
 namespace hvlm {
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s, int reverse);
+                     cudaStream_t s, int reverse, const float* add_rows = nullptr, int add_period = 1);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
 int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv, int n_frames, void* A, const float* cls,
@@ -144,15 +144,16 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
     if (rc) return rc;
     {
         EpiArgs ep;
-        ep.out = hidden;
-        ep.pos = f32(L.pos);
+        ep.out = hidden;      // bare convolution output; the position embedding is added by the pre-LayerNorm kernel
         StageTimer st(HVLM_STAGE_PATCH_GEMM, s);
         rc = launch_gemm(EPI_PATCH, w8 + ws.a_patch, wb + L.patch_w, n_frames * 256, 1024, HVLM_VIT_PATCH_KPAD, ep, s);
         if (rc) return rc;
     }
     {
         StageTimer st(HVLM_STAGE_LAYERNORM, s);
-        rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1);
+        // + position embedding (tokens 1..256; the CLS row got pos[0] from im2col), then pre_layrnorm, in place
+        rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1, f32(L.pos),
+                              HVLM_VIT_TOKENS);
     }
     if (rc) return rc;
 

@@ -16,7 +16,8 @@ namespace hvlm {
 template <typename TOut>
 __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
-                                                            int rows, float eps, int reverse) {
+                                                            int rows, float eps, int reverse,
+                                                            const float* __restrict__ add_rows, int add_period) {
     pdl_launch_dependents();
     pdl_wait();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -27,10 +28,25 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
     float4 v[8];
     float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        v[j] = xr[lane + 32 * j];
-        sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    for (int j = 0; j < 8; ++j) v[j] = xr[lane + 32 * j];
+    if (add_rows != nullptr) {
+        // pre-LayerNorm of the tower: the patch-embedding GEMM stored the bare convolution output, the position
+        // embedding of token t = row % 257 is added here with coalesced reads (token 0 = CLS already carries pos[0])
+        const int t = row % add_period;
+        if (t > 0) {
+            const float4* pr = reinterpret_cast<const float4*>(add_rows + static_cast<size_t>(t) * 1024);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 e = __ldg(pr + lane + 32 * j);
+                v[j].x += e.x;
+                v[j].y += e.y;
+                v[j].z += e.z;
+                v[j].w += e.w;
+            }
+        }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum * (1.0f / 1024.0f);
@@ -69,13 +85,14 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s, int reverse) {
+                     cudaStream_t s, int reverse, const float* add_rows, int add_period) {
     const int grid = (rows + 7) / 8;
     if (out_dtype == HVLM_F32)
-        launch_pdl(layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse);
+        launch_pdl(layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse, add_rows,
+                   add_period);
     else if (out_dtype == HVLM_BF16)
         launch_pdl(layernorm1024_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps,
-                   reverse);
+                   reverse, add_rows, add_period);
     else
         return HVLM_ERR_BAD_DTYPE;
     return check_last("layernorm");
@@ -87,6 +104,11 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
 // contiguously as bf16.  The gy==0 CTA also writes the CLS row  x0[f,0,:] = class_embedding + pos[0].
 // Column order (c, i, j) == conv.weight.reshape(1024, -1).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 template <typename TPix>
 __global__ void __launch_bounds__(256) im2col_kernel(const TPix* __restrict__ pix, __nv_bfloat16* __restrict__ A,
                                                      const float* __restrict__ cls, const float* __restrict__ pos0,
@@ -96,30 +118,43 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TPix* __restrict__ pi
     pdl_wait();
     const int gy = blockIdx.x, f = blockIdx.y;
     const TPix* base = pix + static_cast<size_t>(f) * 3 * 224 * 224;
-    for (int idx = threadIdx.x; idx < 3 * 14 * 224; idx += 256) {
-        const int c = idx / (14 * 224);
-        const int rem = idx - c * 14 * 224;   // i*224 + x
-        slab[idx] = to_float<TPix>(base[static_cast<size_t>(c) * 224 * 224 + (gy * 14) * 224 + rem]);
+    // the 14 image rows of one channel are one contiguous run of 3136 pixels: 16-byte vector loads
+    constexpr int V = Vec16<TPix>::N;
+    constexpr int kRun = 14 * 224;
+    for (int v = threadIdx.x; v < 3 * kRun / V; v += 256) {
+        const int c = v / (kRun / V);
+        const int off = (v - c * (kRun / V)) * V;
+        float fv[V];
+        unpack16<TPix>(ld_stream16(base + static_cast<size_t>(c) * 224 * 224 + gy * kRun + off), fv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) slab[c * kRun + off + e] = fv[e];
     }
     __syncthreads();
     __nv_bfloat16* dst = A + (static_cast<size_t>(f) * 256 + gy * 16) * HVLM_VIT_PATCH_KPAD;
-    for (int idx = threadIdx.x; idx < 16 * (HVLM_VIT_PATCH_KPAD / 2); idx += 256) {
-        const int gx = idx / (HVLM_VIT_PATCH_KPAD / 2);
-        const int col = (idx - gx * (HVLM_VIT_PATCH_KPAD / 2)) * 2;
-        float v0 = 0.f, v1 = 0.f;
-        if (col < HVLM_VIT_PATCH_K) {   // 588 is even: col+1 < 588 as well
-            int c = col / 196, r = col - c * 196;
-            int i = r / 14, j = r - i * 14;
-            v0 = slab[c * 14 * 224 + i * 224 + gx * 14 + j];
-            const int col1 = col + 1;
-            c = col1 / 196;
-            r = col1 - c * 196;
-            i = r / 14;
-            j = r - i * 14;
-            v1 = slab[c * 14 * 224 + i * 224 + gx * 14 + j];
+    // one 16-byte store = 8 consecutive columns (c, i, j) of one patch row
+    for (int v = threadIdx.x; v < 16 * (HVLM_VIT_PATCH_KPAD / 8); v += 256) {
+        const int gx = v / (HVLM_VIT_PATCH_KPAD / 8);
+        const int col0 = (v - gx * (HVLM_VIT_PATCH_KPAD / 8)) * 8;
+        int c = col0 / 196, r = col0 - c * 196;
+        int i = r / 14, j = r - i * 14;
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            o8[e] = (col0 + e < HVLM_VIT_PATCH_K) ? slab[c * kRun + i * 224 + gx * 14 + j] : 0.f;
+            if (++j == 14) {
+                j = 0;
+                if (++i == 14) {
+                    i = 0;
+                    ++c;
+                }
+            }
         }
-        *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<size_t>(gx) * HVLM_VIT_PATCH_KPAD + col) =
-            __floats2bfloat162_rn(v0, v1);
+        uint4 w;
+        w.x = pack_bf16x2(o8[0], o8[1]);
+        w.y = pack_bf16x2(o8[2], o8[3]);
+        w.z = pack_bf16x2(o8[4], o8[5]);
+        w.w = pack_bf16x2(o8[6], o8[7]);
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(gx) * HVLM_VIT_PATCH_KPAD + col0) = w;
     }
     if (gy == 0) {
         float* o = x0 + static_cast<size_t>(f) * HVLM_VIT_TOKENS * 1024;
@@ -269,7 +304,7 @@ extern "C" int hvlm_layernorm_1024(const float* x, const float* gamma, const flo
     using namespace hvlm;
     if (!x || !gamma || !beta || !out || rows <= 0) return HVLM_ERR_BAD_ARG;
     if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(out)) return HVLM_ERR_ALIGN;
-    return launch_layernorm(x, gamma, beta, out, rows, out_dtype, eps, static_cast<cudaStream_t>(stream), 0);
+    return launch_layernorm(x, gamma, beta, out, rows, out_dtype, eps, static_cast<cudaStream_t>(stream), 0, nullptr, 1);
 }
 
 extern "C" int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls,
