@@ -224,17 +224,36 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
     ``im_start_end``: the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch of llava_arch.py:146-161,172-181."""
     table = host.get_model().embed_tokens.weight
     B, T = input_ids.shape
-    n_img, Nv, D = visual.shape
+    slot_offsets = None
+    if isinstance(visual, (list, tuple)):
+        # per-slot token blocks of different lengths (list path of images_to_tokens): row-concatenate and describe the
+        # slots by their row offsets (sizes are host-known shapes: no sync)
+        sizes = [int(v.shape[0]) for v in visual]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        slot_offsets = torch.tensor(offs, dtype=torch.int32, device=input_ids.device)
+        visual = torch.cat(list(visual), dim=0).unsqueeze(0)            # [1, sum n, D]
+        n_img, Nv, D = len(sizes), 1, visual.shape[2]
+    else:
+        n_img, Nv, D = visual.shape
+        sizes = None
     if visual.dtype != table.dtype:
         visual = visual.to(table.dtype)
-    static = bool(getattr(host.config, "hvlm_static_splice", False))
+    static = bool(getattr(host.config, "hvlm_static_splice", False)) and sizes is None
     counts = ops.splice_count(input_ids)
     if static:
         # collator contract (hybrid_dataset.py:155-158): exactly one image token per sample, equal T
         Lout, uniform = T - 1 + Nv, True
     else:
         ks = counts.tolist()                                         # the ONE host sync of the general path
-        lens = [T + k * (Nv - 1) for k in ks]
+        if sizes is None:
+            lens = [T + k * (Nv - 1) for k in ks]
+        else:
+            lens, slot = [], 0
+            for k in ks:                                             # a sample without image token still uses a slot
+                lens.append(T - k + sum(sizes[slot:slot + k]))
+                slot += max(k, 1)
         Lout, uniform = max(lens), all(n == lens[0] for n in lens)
     hand_mode, n_hand = 0, 0
     if variant == L.SPLICE_HANDSONVLM:
@@ -246,7 +265,7 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
         elif future_hands is not None:
             hand_mode, n_hand = 2, int(future_hands.shape[2])
     src_index, hand_code, lens_d, hand_scale, status = ops.splice_plan(
-        input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand)
+        input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand, slot_offsets)
     if not static:
         _raise_on_status(int(status.item()))
     else:
@@ -316,9 +335,9 @@ class LlavaMetaForCausalLM(ABC):
         ise = bool(getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False))
         image_features = self.visual_to_tokens(images)
         if isinstance(image_features, (list, tuple)):
-            if any(x.shape != image_features[0].shape for x in image_features):
-                raise NotImplementedError("per-image variable token counts are not supported by the splice kernel")
-            image_features = torch.stack(list(image_features), 0)
+            if all(x.shape == image_features[0].shape for x in image_features):
+                image_features = torch.stack(list(image_features), 0)
+            # else: token blocks of different lengths go to the splice as a list (ragged plan)
         new_mask, embeds, new_labels = splice_tokens(self, L.SPLICE_LLAVA, input_ids, attention_mask, labels,
                                                      image_features, im_start_end=ise)
         return None, new_mask, past_key_values, embeds, new_labels

@@ -34,12 +34,14 @@ __global__ void splice_count_kernel(const int64_t* __restrict__ ids, int T, int3
 }
 
 __global__ void __launch_bounds__(kPlanThreads)
-splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ counts, int B, int T, int Nv,
+splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
+                   const int32_t* __restrict__ slot_offsets /* NULL: every slot has Nv rows */, int B, int T, int Nv,
                    int n_img, int L, int vocab, int variant, int hand_mode, int n_hand_points,
                    int32_t* __restrict__ src_index, int8_t* __restrict__ hand_code, int32_t* __restrict__ lens,
                    float* __restrict__ hand_scale, int32_t* __restrict__ status) {
     __shared__ int scan_smem[9];
     __shared__ int img_pos[kMaxImgPerSample];
+    __shared__ int cum[kMaxImgPerSample + 1];   // cum[m] = rows added by the first m image tokens of this sample
     const int b = blockIdx.x;
     const int64_t* row = ids + static_cast<int64_t>(b) * T;
     int32_t* dst = src_index + static_cast<int64_t>(b) * L;
@@ -50,10 +52,25 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     int slot0 = 0;
     for (int i = 0; i < b; ++i) slot0 += max(counts[i], 1);
     const int k_img = counts[b];
-    const int len = T + k_img * (Nv - 1);
+    const int n_fill = min(k_img, kMaxImgPerSample);
+    // rows of visual slot g: uniform Nv, or slot_offsets[g+1] - slot_offsets[g] when the caller hands in per-sample token
+    // blocks of different lengths (the list path of images_to_tokens, llava_arch.py:95-106)
+    auto nv_of = [&](int g) { return slot_offsets ? (g < n_img ? slot_offsets[g + 1] - slot_offsets[g] : 0) : Nv; };
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int j = 0; j < n_fill; ++j) {
+            cum[j] = c;
+            c += nv_of(slot0 + j) - 1;
+        }
+        cum[n_fill] = c;
+    }
+    __syncthreads();
+    const int len = T + cum[n_fill];
+    int len0 = T;
+    for (int j = 0; j < min(counts[0], kMaxImgPerSample); ++j) len0 += nv_of(j) - 1;
     if (len > L) err |= HVLM_PLAN_ERR_LEN_OVERFLOW;
     if (slot0 + max(k_img, 1) > n_img || k_img > kMaxImgPerSample) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
-    if (len != T + counts[0] * (Nv - 1)) err |= HVLM_PLAN_NOT_UNIFORM;
+    if (len != len0) err |= HVLM_PLAN_NOT_UNIFORM;
 
     // defaults: padding + no hand code
     for (int r = threadIdx.x; r < L; r += blockDim.x) {
@@ -70,7 +87,7 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
         int total;
         const int before = img_seen + block_excl_scan(is_img, &total, scan_smem);
         if (p < T) {
-            const int opos = p + before * (Nv - 1);
+            const int opos = p + cum[min(before, n_fill)];
             if (is_img) {
                 if (before < kMaxImgPerSample) img_pos[before] = p;
             } else {
@@ -84,11 +101,11 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     __syncthreads();
 
     // visual rows
-    const int n_fill = min(k_img, kMaxImgPerSample);
     for (int j = 0; j < n_fill; ++j) {
-        const int o0 = img_pos[j] + j * (Nv - 1);
-        const int g0 = (slot0 + j) * Nv;
-        for (int r = threadIdx.x; r < Nv; r += blockDim.x)
+        const int o0 = img_pos[j] + cum[j];
+        const int g0 = slot_offsets ? (slot0 + j < n_img ? slot_offsets[slot0 + j] : 0) : (slot0 + j) * Nv;
+        const int nv = nv_of(slot0 + j);
+        for (int r = threadIdx.x; r < nv; r += blockDim.x)
             if (o0 + r < L) dst[o0 + r] = -(1 + g0 + r);
     }
 
@@ -97,7 +114,7 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     float scale = 0.f;
     if (variant == HVLM_SPLICE_HANDSONVLM && hand_mode != 0 && k_img > 0 && k_img <= kMaxImgPerSample) {
         const int tail0 = img_pos[k_img - 1] + 1;            // first tail position
-        const int shift = k_img * (Nv - 1);                   // output row = p + shift
+        const int shift = cum[k_img];                         // output row = p + shift
         int seen = 0;
         for (int p0 = tail0; p0 < T; p0 += kPlanThreads) {
             const int p = p0 + threadIdx.x;
@@ -247,9 +264,10 @@ extern "C" int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* coun
     return check_last("splice_count");
 }
 
-extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B, int T, int Nv, int n_img, int L,
-                                int vocab, int variant, int hand_mode, int n_hand_points, int32_t* src_index,
-                                int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status, void* stream) {
+static int splice_plan_impl(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B, int T, int Nv,
+                            int n_img, int L, int vocab, int variant, int hand_mode, int n_hand_points,
+                            int32_t* src_index, int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status,
+                            void* stream) {
     using namespace hvlm;
     if (!ids || !counts || !src_index || !hand_code || !lens || !status) return HVLM_ERR_BAD_ARG;
     if (B <= 0 || T <= 0 || Nv <= 0 || n_img <= 0 || L <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
@@ -258,9 +276,25 @@ extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B
     if (hand_mode < 0 || hand_mode > 2 || n_hand_points < 0 || n_hand_points > 127) return HVLM_ERR_BAD_ARG;
     StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_plan_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        ids, counts, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index, hand_code, lens,
-        hand_scale, status);
+        ids, counts, slot_offsets, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index, hand_code,
+        lens, hand_scale, status);
     return check_last("splice_plan");
+}
+
+extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B, int T, int Nv, int n_img, int L,
+                                int vocab, int variant, int hand_mode, int n_hand_points, int32_t* src_index,
+                                int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status, void* stream) {
+    return splice_plan_impl(ids, counts, nullptr, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index,
+                            hand_code, lens, hand_scale, status, stream);
+}
+
+extern "C" int hvlm_splice_plan_ragged(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B,
+                                       int T, int n_slots, int L, int vocab, int variant, int hand_mode,
+                                       int n_hand_points, int32_t* src_index, int8_t* hand_code, int32_t* lens,
+                                       float* hand_scale, int32_t* status, void* stream) {
+    if (!slot_offsets) return HVLM_ERR_BAD_ARG;
+    return splice_plan_impl(ids, counts, slot_offsets, B, T, 1, n_slots, L, vocab, variant, hand_mode, n_hand_points,
+                            src_index, hand_code, lens, hand_scale, status, stream);
 }
 
 extern "C" int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens,

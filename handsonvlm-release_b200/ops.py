@@ -374,7 +374,9 @@ def splice_count(ids: torch.Tensor) -> torch.Tensor:
 
 
 def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lout: int, vocab: int, variant: int,
-                hand_mode: int, n_hand: int):
+                hand_mode: int, n_hand: int, slot_offsets: Optional[torch.Tensor] = None):
+    """``slot_offsets`` (int32 [n_img+1], device): per-slot row ranges of a row-concatenated visual tensor, for visual
+    token blocks of different lengths (``Nv`` is ignored then)."""
     ids = ids.contiguous()
     B, T = ids.shape
     dev = ids.device
@@ -383,6 +385,13 @@ def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lo
     lens = torch.empty(B, dtype=torch.int32, device=dev)
     hand_scale = torch.empty(B, dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if slot_offsets is not None:
+        assert slot_offsets.dtype == torch.int32 and slot_offsets.numel() == n_img + 1 and slot_offsets.is_cuda
+        L.check(L.lib().hvlm_splice_plan_ragged(_p(ids), _p(counts), _p(slot_offsets.contiguous()), B, T, n_img, Lout,
+                                                vocab, variant, hand_mode, n_hand, _p(src_index), _p(hand_code),
+                                                _p(lens), _p(hand_scale), _p(status), _stream()),
+                "hvlm_splice_plan_ragged")
+        return src_index, hand_code, lens, hand_scale, status
     L.check(L.lib().hvlm_splice_plan(_p(ids), _p(counts), B, T, Nv, n_img, Lout, vocab, variant, hand_mode, n_hand,
                                      _p(src_index), _p(hand_code), _p(lens), _p(hand_scale), _p(status), _stream()),
             "hvlm_splice_plan")

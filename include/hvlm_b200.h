@@ -219,6 +219,14 @@ HVLM_API int hvlm_splice_plan(const int64_t* ids, const int32_t* counts /*from h
                      int hand_mode /*0 none, 1 training (4 points, cnt/4 scaling), 2 eval (n points)*/,
                      int n_hand_points, int32_t* src_index, int8_t* hand_code, int32_t* lens,
                      float* hand_scale /*[B]*/, int32_t* status, void* stream);
+/* Same plan for visual token blocks of DIFFERENT lengths per image slot -- the list path of images_to_tokens
+ * (llava_arch.py:95-106: each sample's image group becomes one flat [n_i*256, D] block and its single image token expands to
+ * all of it).  slot_offsets int32 [n_slots+1] (device): rows of slot g are visual[slot_offsets[g] .. slot_offsets[g+1]) of
+ * the row-concatenated visual tensor that hvlm_splice_fwd / _bwd receive. */
+HVLM_API int hvlm_splice_plan_ragged(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B, int T,
+                            int n_slots, int L, int vocab, int variant, int hand_mode, int n_hand_points,
+                            int32_t* src_index, int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status,
+                            void* stream);
 HVLM_API int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens, const float* hand_scale,
                     const int64_t* ids, const int64_t* labels /*NULL ok*/, const uint8_t* mask /*NULL ok*/,
                     const void* embed_table, const void* visual, const uint8_t* visual_mask /*NULL = all true*/,

@@ -282,6 +282,29 @@ def golden_splice_hvlm_im_start_end(ns):
          embeds=e2.detach(), labels=l2, t=t, has_last_visual_token_index=hasattr(host, "last_visual_token_index"))
 
 
+@torch.no_grad()
+def golden_splice_llava_list(ns):
+    """The list path of images_to_tokens (llava_arch.py:95-106): per-sample image groups of DIFFERENT sizes; each
+    sample's single image token expands to its whole group (n_i * 256 tokens), so the batch is ragged."""
+    sd, proj, emb = small_parts()
+    tower = ref_shim.build_tower(ns, hf_model(SMALL, sd), select_layer=-2)
+    LV = ns.llava_arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal
+    cfg = types.SimpleNamespace(input_type="image")
+    ids, mask, labels = synth.prompt_llava(seed=34)
+    ids = torch.cat([ids, ids, ids], 0).clone()
+    ids[1, 5:9] = torch.arange(200, 204)
+    ids[2, 35] = 99                                   # sample 2 has no image token (still consumes a slot)
+    labels = torch.arange(ids.numel(), dtype=torch.int64).reshape(ids.shape) + 2000
+    mask = torch.ones_like(ids, dtype=torch.bool)
+    mask[1, -4:] = False
+    groups = [synth.pixels((1, 3, 224, 224), seed=18), synth.pixels((3, 3, 224, 224), seed=19),
+              synth.pixels((2, 3, 224, 224), seed=20)]
+    host = make_host(ns, ns.lita_arch.LitaMetaForCausalLM, tower, proj, emb, cfg, ids.shape[0])
+    r_ids, m2, _, e2, l2 = LV(host, ids, mask, None, labels, groups)
+    save("splice_llava_list_ragged", ids=ids, in_mask=mask, in_labels=labels, mask=m2, embeds=e2, labels=l2,
+         group_sizes=[g.shape[0] for g in groups])
+
+
 def golden_gather(ns):
     """Execute the reference's inline gather (handsonvlm.py, inside forward) from its source text."""
     import inspect
@@ -362,6 +385,7 @@ def main():
     golden_splice(ns)
     golden_splice_im_start_end(ns)
     golden_splice_hvlm_im_start_end(ns)
+    golden_splice_llava_list(ns)
     golden_vit_full(ns)
 
 

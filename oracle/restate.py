@@ -191,15 +191,19 @@ def hand_pos_embedding(gt_hand: torch.Tensor, D: int) -> torch.Tensor:
 # a5 / a6: splice plans
 # ----------------------------------------------------------------------------------------
 
-def splice_plan(ids_row: torch.Tensor, Nv: int):
+def splice_plan(ids_row: torch.Tensor, Nv):
     """Source plan for one sample: list of (kind, index) per output row.
     kind 0 = text row (index = position in ids_row), kind 1 = visual row (index = j-th image
-    token of this sample * Nv + offset).  A sample with no IMAGE_TOKEN_INDEX maps 1:1."""
+    token of this sample * Nv + offset; with a list ``Nv`` of per-image row counts the index is the pair
+    (j, offset)).  A sample with no IMAGE_TOKEN_INDEX maps 1:1."""
     out = []
     j = 0
     for pos, tok in enumerate(ids_row.tolist()):
         if tok == IMAGE_TOKEN_INDEX:
-            out.extend((1, j * Nv + r) for r in range(Nv))
+            if isinstance(Nv, int):
+                out.extend((1, j * Nv + r) for r in range(Nv))
+            else:
+                out.extend((1, (j, r)) for r in range(Nv[j]))
             j += 1
         else:
             out.append((0, pos))
@@ -227,11 +231,16 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
     consecutive slots; a sample with none still consumes one (llava_arch.py:135, handsonvlm.py:243).
     """
     B, T = ids.shape
-    Nv, D = visual.shape[1], visual.shape[2]
+    ragged = isinstance(visual, (list, tuple))          # per-slot blocks [n_g, D] (list path of images_to_tokens)
+    Nv, D = (None, visual[0].shape[-1]) if ragged else (visual.shape[1], visual.shape[2])
     rows_e, rows_l, rows_m = [], [], []
     slot = 0
     for b in range(B):
-        plan, k_img = splice_plan(ids[b], Nv)
+        if ragged:
+            k_here = int((ids[b] == IMAGE_TOKEN_INDEX).sum())
+            plan, k_img = splice_plan(ids[b], [int(visual[slot + j].shape[0]) for j in range(k_here)])
+        else:
+            plan, k_img = splice_plan(ids[b], Nv)
         e = torch.empty(len(plan), D, dtype=embed_w.dtype)
         lab = torch.empty(len(plan), dtype=torch.int64) if labels is not None else None
         msk = torch.empty(len(plan), dtype=torch.bool) if attention_mask is not None else None
@@ -245,12 +254,12 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
                     # only the HandsOnVLM splice builds its mask by position (handsonvlm.py:283)
                     msk[r] = attention_mask[b, idx - 1 if (after_img and variant == "handsonvlm") else idx]
             else:
-                img = slot + idx // Nv
-                e[r] = visual[img, idx % Nv]
+                img, off = (slot + idx[0], idx[1]) if ragged else (slot + idx // Nv, idx % Nv)
+                e[r] = visual[img][off]
                 if lab is not None:
                     lab[r] = IGNORE_INDEX
                 if msk is not None:
-                    msk[r] = True if visual_mask is None else visual_mask[img, idx % Nv]
+                    msk[r] = True if visual_mask is None else visual_mask[img][off]
         if variant == "handsonvlm" and k_img > 0 and not im_start_end:     # (:343-344: that branch adds nothing)
             # tail segment = text after the last image token (handsonvlm.py:342-396)
             last_img_pos = int(torch.where(ids[b] == IMAGE_TOKEN_INDEX)[0][-1])

@@ -389,6 +389,32 @@ def test_splice_hvlm_im_start_end_variant(golden, small):
     assert torch.equal(e2.cpu(), ro[1])
 
 
+def test_splice_llava_list_of_image_groups(golden, small):
+    """Ragged visual token blocks (list path of images_to_tokens, llava_arch.py:95-106) through hvlm_splice_plan_ragged:
+    labels / mask bit-exact against the reference fixture, rows exact copies, gradient reaches every block."""
+    g = golden("splice_llava_list_ragged")
+    sd, proj, emb = small
+    blocks = []
+    for n, sd_ in zip(g["group_sizes"], (18, 19, 20)):
+        feats = restate.tower_forward(synth.pixels((int(n), 3, 224, 224), seed=sd_), sd, -2, SMALL)
+        blocks.append(restate.project(feats, proj.weight.data, proj.bias.data).reshape(-1, SMALL_D))
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=emb.weight.data.to(DEV))),
+        config=types.SimpleNamespace(hvlm_static_splice=True))       # static mode is ignored for ragged blocks
+    dblocks = [b.to(DEV).requires_grad_(True) for b in blocks]
+    m2, e2, l2 = arch.splice_tokens(host, L.SPLICE_LLAVA, T(g["ids"]).to(DEV), T(g["in_mask"]).to(DEV),
+                                    T(g["in_labels"]).to(DEV), dblocks)
+    assert e2.shape == tuple(g["embeds"].shape)
+    assert torch.equal(l2.cpu(), T(g["labels"])) and torch.equal(m2.cpu(), T(g["mask"]))
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+    ro = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), blocks, emb.weight.data, "llava")
+    assert torch.equal(e2.detach().cpu(), ro[1])
+    # backward: sample 0 uses block 0, sample 1 block 1; block 2 belongs to the sample without an image token
+    e2.sum().backward()
+    assert float(dblocks[0].grad.min()) == 1.0 and float(dblocks[1].grad.min()) == 1.0
+    assert float(dblocks[2].grad.abs().max()) == 0.0
+
+
 def test_splice_static_mode_no_sync_and_status_flag():
     D = 256
     table = synth.embed_table(D)
@@ -653,6 +679,35 @@ def test_llava_config1_single_image_fp32(tower23):
     r = host.prepare_inputs_labels_for_multimodal(torch.tensor([[5]], device=DEV), torch.ones(1, 1, dtype=torch.bool, device=DEV),
                                                   pkv, None, px.to(DEV))
     assert r[3] is None and r[1].shape == (1, 10)
+
+
+def test_llava_list_of_image_groups_end_to_end(tower23):
+    """LLaVA list input (images_to_tokens list path): groups of 1 and 2 images through ONE tower call, ragged splice."""
+    tw, sd = tower23("hf")
+    D = 4096
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    host = _host(arch.LitaMetaForCausalLM, tw, proj, emb, types.SimpleNamespace(input_type="image"), 2)
+    groups = [synth.pixels((1, 3, 224, 224), seed=21), synth.pixels((2, 3, 224, 224), seed=22)]
+    ids, mask, labels = synth.prompt_llava(seed=35)
+    ids = torch.cat([ids, ids], 0)
+    mask = torch.cat([mask, mask], 0)
+    labels = torch.cat([labels, labels], 0)
+    with torch.no_grad():
+        r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV),
+                                                      [g.to(DEV) for g in groups])
+    m2, e2, l2 = r[1], r[3], r[4]
+    blocks = [restate.project(restate.tower_forward(g, sd, -2), ps["mm_projector.weight"],
+                              ps["mm_projector.bias"]).reshape(-1, D) for g in groups]
+    rm, re_, rl = restate.splice(ids, mask, labels, blocks, synth.embed_table(D), "llava")
+    T_in = ids.shape[1]
+    assert e2.shape == (2, T_in - 1 + 512, D) == tuple(re_.shape)
+    assert torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm)
+    assert relmax(e2, re_) <= TOL_BF16
 
 
 def test_lita_videos_to_tokens_archs(tower23):

@@ -231,6 +231,26 @@ def test_splice_hvlm_im_start_end(golden, small):
     assert not bool(g["has_last_visual_token_index"])
 
 
+def _list_visual(small, sizes, seeds=(18, 19, 20)):
+    sd, pw, pb = small[0], small[1], small[2]
+    blocks = []
+    for n, sd_ in zip(sizes, seeds):
+        feats = restate.tower_forward(synth.pixels((int(n), 3, 224, 224), seed=sd_), sd, -2, SMALL)
+        blocks.append(restate.project(feats, pw, pb).reshape(-1, pw.shape[0]))       # [n*256, D]
+    return blocks
+
+
+def test_splice_llava_list_of_image_groups(golden, small):
+    """images_to_tokens list path (llava_arch.py:95-106): groups of 1 / 3 / 2 images -> token blocks of 256 / 768 / 512
+    rows, one image token per sample expands to its whole block; the third sample has no image token."""
+    g = golden("splice_llava_list_ragged")
+    blocks = _list_visual(small, g["group_sizes"])
+    m2, e2, l2 = restate.splice(T(g["ids"]), T(g["in_mask"]), T(g["in_labels"]), blocks, small[3], "llava")
+    assert e2.shape == tuple(g["embeds"].shape)
+    assert torch.equal(l2, T(g["labels"])) and torch.equal(m2, T(g["mask"]))
+    assert relmax(e2, T(g["embeds"])) <= 2e-5
+
+
 def test_splice_cfg1_shapes(golden):
     g = golden("splice_llava_cfg1")
     assert g["embeds"].shape == (1, 311, SMALL_D)
