@@ -25,7 +25,7 @@ def __getattr__(name):
                 "gather_hand_traj_states"):
         from . import arch
         return getattr(arch, name)
-    if name == "CVAETrajDecoder":
-        from .traj_decoder import CVAETrajDecoder
-        return CVAETrajDecoder
+    if name in ("CVAETrajDecoder", "MLPTrajDecoder"):
+        from . import traj_decoder
+        return getattr(traj_decoder, name)
     raise AttributeError(name)

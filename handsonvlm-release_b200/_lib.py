@@ -68,6 +68,7 @@ SIGNATURES = {
     "hvlm_hand_gather_step": (i32, [p, i32, i32, i32, p, p]),
     "hvlm_traj_decode_workspace_bytes": (sz, [i32, i32]),
     "hvlm_traj_decode": (i32, [p, i64, i32, p, p, p, p, p, i32, i32, i32, i32, i32, p, p, sz, p]),
+    "hvlm_skinny_linear": (i32, [p, i64, p, p, i32, i32, i32, i32, i32, p, p]),
     "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
     "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
     "hvlm_launch_count": (C.c_uint64, []),

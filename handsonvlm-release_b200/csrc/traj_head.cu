@@ -192,6 +192,91 @@ traj_decode_kernel(const T* __restrict__ cond, int64_t ld_cond, int interleaved,
     if (threadIdx.x == 0) counter[blockIdx.y] = 0;      // ready for the next call on this stream
 }
 
+// out[r, j] = act(b[j] + W[j, :] . x[r, :]) for a handful of rows: one output unit per warp, all 16-byte weight loads of the
+// row in flight, activations staged once per CTA as fp32.  The building block of the MLP trajectory decoder
+// (hoi_forecast/architecture/traj_decoder.py:94-104: Linear-ReLU-Linear-ReLU-Linear on R = 2B rows).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+skinny_linear_kernel(const T* __restrict__ x, int64_t ld_x, const T* __restrict__ W, const T* __restrict__ b,
+                     T* __restrict__ out, int R, int K, int H, int act, int vec_ok) {
+    extern __shared__ __align__(16) float xs[];                       // [kRows][K] fp32
+    constexpr int V = Vec16<T>::N;
+    const int r0 = blockIdx.y * kRows;
+    const int nrows = min(kRows, R - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kWarps + warp;
+    const bool live = j < H;
+    const T* wrow = W + static_cast<int64_t>(live ? j : 0) * K;
+    uint4 wv[kInFlight];
+#pragma unroll
+    for (int it = 0; it < kInFlight; ++it) {
+        const int i0 = (it * 32 + lane) * V;
+        if (live && i0 < K) wv[it] = ld_stream16(wrow + i0);
+    }
+    if (vec_ok) {
+        const int kv = K / V;
+        for (int v = threadIdx.x; v < nrows * kv; v += kThreads) {
+            const int rr = v / kv, c = (v - rr * kv) * V;
+            float f[V];
+            unpack16<T>(*reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r0 + rr) * ld_x + c), f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) xs[rr * K + c + e] = f[e];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < nrows * K; idx += kThreads) {
+            const int rr = idx / K;
+            xs[idx] = to_float<T>(x[static_cast<int64_t>(r0 + rr) * ld_x + (idx - rr * K)]);
+        }
+    }
+    __syncthreads();
+    float acc[kRows];
+#pragma unroll
+    for (int rr = 0; rr < kRows; ++rr) acc[rr] = 0.f;
+    if (live) {
+        for (int base = 0; base < K; base += kInFlight * 32 * V) {
+            if (base > 0) {
+#pragma unroll
+                for (int it = 0; it < kInFlight; ++it) {
+                    const int i0 = base + (it * 32 + lane) * V;
+                    if (i0 < K) wv[it] = ld_stream16(wrow + i0);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < kInFlight; ++it) {
+                const int i0 = base + (it * 32 + lane) * V;
+                if (i0 < K) {
+                    float w[V];
+                    unpack16<T>(wv[it], w);
+#pragma unroll
+                    for (int rr = 0; rr < kRows; ++rr) {
+                        if (rr < nrows) {
+#pragma unroll
+                            for (int e = 0; e < V; ++e) acc[rr] = fmaf(w[e], xs[rr * K + i0 + e], acc[rr]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kRows; ++rr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], o);
+    }
+    if (lane == 0 && live) {
+        const float bj = b ? to_float<T>(b[j]) : 0.f;
+#pragma unroll
+        for (int rr = 0; rr < kRows; ++rr) {
+            if (rr < nrows) {
+                float a = acc[rr] + bj;
+                if (act == 1) a = fmaxf(a, 0.f);
+                else if (act == 2) a = a > 0.f ? a : expm1f(a);
+                out[static_cast<int64_t>(r0 + rr) * H + j] = from_float<T>(a);
+            }
+        }
+    }
+}
+
 inline int grid_x(int H) { return (H + kWarps - 1) / kWarps; }
 inline int grid_y(int R) { return (R + kRows - 1) / kRows; }
 // workspace layout: [0, kCounterBytes) one arrival counter per row chunk (always at the same place, so the "left
@@ -250,4 +335,30 @@ extern "C" int hvlm_traj_decode(const void* cond, int64_t ld_cond, int interleav
         }
     });
     return check_last("traj_decode");
+}
+
+extern "C" int hvlm_skinny_linear(const void* x, int64_t ld_x, const void* W, const void* b, int act, int dtype, int R,
+                                  int K, int H, void* out, void* stream) {
+    using namespace hvlm;
+    using namespace hvlm::traj;
+    if (!x || !W || !out) return HVLM_ERR_BAD_ARG;
+    if (R <= 0 || K <= 0 || H <= 0 || ld_x < K || act < 0 || act > 2) return HVLM_ERR_BAD_SHAPE;
+    const int elt = dtype == HVLM_F32 ? 4 : 2;
+    if ((K * elt) % 16 != 0 || (reinterpret_cast<uintptr_t>(W) & 15u)) return HVLM_ERR_ALIGN;
+    const size_t smem = static_cast<size_t>(kRows) * K * sizeof(float);
+    if (smem > 200 * 1024) return HVLM_ERR_UNSUPPORTED;
+    const int V = 16 / elt;
+    const int vec_ok = (ld_x % V == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_GATHER, s);
+    HVLM_DISPATCH_DTYPE(dtype, TT, {
+        auto kern = skinny_linear_kernel<TT>;
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return HVLM_ERR_CUDA;
+        kern<<<dim3(grid_x(H), grid_y(R)), kThreads, smem, s>>>(static_cast<const TT*>(x), ld_x, static_cast<const TT*>(W),
+                                                              static_cast<const TT*>(b), static_cast<TT*>(out), R, K, H,
+                                                              act, vec_ok);
+    });
+    return check_last("skinny_linear");
 }

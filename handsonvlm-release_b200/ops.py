@@ -601,6 +601,24 @@ def traj_decode(cond: torch.Tensor, z: torch.Tensor, w1: torch.Tensor, b1: torch
     return out
 
 
+def skinny_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: str = "none") -> torch.Tensor:
+    """``act(x W^T + b)`` for a handful of rows (one warp per output unit, fp32 accumulate): the layers of the MLP trajectory
+    decoder in the generation loop.  x [R,K], w [H,K] -> [R,H] in x.dtype."""
+    _need_cuda(x, w)
+    ensure_device()
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    w = w.to(x.dtype).contiguous()
+    b = None if b is None else b.to(x.dtype).contiguous()
+    R, K = x.shape
+    H = w.shape[0]
+    out = torch.empty(R, H, dtype=x.dtype, device=x.device)
+    L.check(L.lib().hvlm_skinny_linear(_p(x), x.stride(0), _p(w), _p(b), {"none": 0, "relu": 1, "elu": 2}[act], _dt(x),
+                                       R, K, H, _p(out), _stream()), "hvlm_skinny_linear")
+    return out
+
+
 def hand_gather_step(hidden_last: torch.Tensor) -> torch.Tensor:
     """Generation-time gather (handsonvlm.py:613-616): [B,D] -> [B,2,1,D/2]."""
     _need_cuda(hidden_last)

@@ -98,3 +98,48 @@ class CVAETrajDecoder(nn.Module):
         ``hidden_states[-1][:, -1, :]`` [B, D] -> ``pred_hand`` [B, 2, 2]."""
         B = hidden_last.shape[0]
         return self.hand_traj_decoder.inference_step(hidden_last, z=z).reshape(B, 2, 2)
+
+
+class _TrajMLP(nn.Module):
+    """``TrajMLP`` parameters (hoi_forecast/architecture/traj_decoder.py:94-104)."""
+
+    def __init__(self, hidden_dim, token_dim):
+        super().__init__()
+        self.token_dim = token_dim
+        self.mlp = nn.Sequential(nn.Linear(token_dim, hidden_dim), nn.ReLU(inplace=True),
+                                 nn.Linear(hidden_dim, hidden_dim), nn.ReLU(inplace=True), nn.Linear(hidden_dim, 2))
+
+    @torch.no_grad()
+    def inference(self, hand_embedding, contact_point=None):
+        R = hand_embedding.shape[0]
+        assert hand_embedding.shape == torch.Size([R, self.token_dim]), hand_embedding.shape
+        m = self.mlp
+        h = ops.skinny_linear(hand_embedding, m[0].weight, m[0].bias, "relu")
+        h = ops.skinny_linear(h, m[2].weight, m[2].bias, "relu")
+        return ops.skinny_linear(h, m[4].weight, m[4].bias, "none")
+
+
+class MLPTrajDecoder(nn.Module):
+    """Drop-in for ``MLPTrajDecoder(token_dim)`` (handsonvlm/model/language_model/traj_decoder.py:50-57), generation side:
+    same state-dict keys (``hand_traj_decoder.mlp.{0,2,4}``), same ``inference(pred_hand_embeddings=...)`` call."""
+
+    def __init__(self, token_dim, hidden_dim=512):
+        super().__init__()
+        self.token_dim = token_dim
+        self.hand_traj_decoder = _TrajMLP(hidden_dim, token_dim)
+
+    def forward(self, **kwargs):
+        raise NotImplementedError("training-side losses are outside the visual-token path this library replaces; keep the "
+                                  "reference module for training")
+
+    def inference(self, **kwargs):
+        e = kwargs["pred_hand_embeddings"]
+        B, T_pred = e.shape[0], e.shape[2]
+        assert e.shape == torch.Size([B, 2, T_pred, self.token_dim]), e.shape
+        return self.hand_traj_decoder.inference(e.reshape(-1, self.token_dim)).reshape(B, 2, T_pred, 2)
+
+    def inference_step(self, hidden_last):
+        """``hidden_states[-1][:, -1, :]`` [B, D] -> ``pred_hand`` [B, 2, 2] (handsonvlm.py:609-622)."""
+        B = hidden_last.shape[0]
+        e = ops.hand_gather_step(hidden_last)                     # [B,2,1,D/2]
+        return self.inference(pred_hand_embeddings=e).reshape(B, 2, 2)

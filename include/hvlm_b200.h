@@ -272,6 +272,13 @@ HVLM_API int hvlm_traj_decode(const void* cond, int64_t ld_cond, int interleaved
                      const void* W2, const void* b2, int dtype, int R, int Dc, int L, int H, float* out, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* out[r, j] = act(b[j] + W[j, :] . x[r, :]) for a handful of rows (R = 2B in the generation loop): the layers of the MLP
+ * trajectory decoder, TrajMLP.inference  hoi_forecast/architecture/traj_decoder.py:94-104,139-147  (Linear-ReLU-Linear-
+ * ReLU-Linear).  x [R, K] with row stride ld_x, W [H, K], b [H] or NULL, out [R, H]; all in `dtype`, fp32 accumulation.
+ * act: 0 none, 1 ReLU, 2 ELU. */
+HVLM_API int hvlm_skinny_linear(const void* x, int64_t ld_x, const void* W, const void* b, int act, int dtype, int R, int K,
+                       int H, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * helpers for the training-shaped variant
  * ---------------------------------------------------------------------------------------------- */

@@ -370,6 +370,11 @@ def golden_traj(ns):
         torch.manual_seed(77)
         z = dec.hand_traj_decoder.z_scale * torch.randn([2, 256])
         save("traj_step", out=out, z=z)
+        # the MLP decoder (traj_decoder 'MLP'): deterministic
+        mlp = mod.MLPTrajDecoder(token_dim=Dc)
+        mlp.load_state_dict(synth.traj_mlp_state(Dc, seed=4), strict=True)
+        emb = synth.gen("trajmlp_emb", (3, 2, 4, Dc), 1.0, seed=53)
+        save("traj_mlp_infer", out=mlp.inference(pred_hand_embeddings=emb))
 
 
 def main():

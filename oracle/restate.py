@@ -411,6 +411,19 @@ def traj_decoder_inference(pred_hand_embeddings: torch.Tensor, z: torch.Tensor, 
     return traj_cvae_inference(pred_hand_embeddings.reshape(-1, Dc), z, sd).reshape(B, 2, T_pred, 2)
 
 
+def traj_mlp_inference(pred_hand_embeddings: torch.Tensor, sd: dict) -> torch.Tensor:
+    """``MLPTrajDecoder.inference`` (traj_decoder.py:39-47 -> ``TrajMLP.inference``,
+    hoi_forecast/architecture/traj_decoder.py:139-147): Linear-ReLU-Linear-ReLU-Linear on the rows (b, hand, k).
+    [B,2,T_pred,token_dim] -> [B,2,T_pred,2]."""
+    pre = "hand_traj_decoder.mlp."
+    B, _, T_pred, Dc = pred_hand_embeddings.shape
+    h = pred_hand_embeddings.reshape(-1, Dc).float()
+    h = torch.relu(h @ sd[pre + "0.weight"].float().t() + sd[pre + "0.bias"].float())
+    h = torch.relu(h @ sd[pre + "2.weight"].float().t() + sd[pre + "2.bias"].float())
+    h = h @ sd[pre + "4.weight"].float().t() + sd[pre + "4.bias"].float()
+    return h.reshape(B, 2, T_pred, 2)
+
+
 def traj_decode_step(hidden_last: torch.Tensor, z: torch.Tensor, sd: dict) -> torch.Tensor:
     """The generation loop's ``<hand_traj>`` branch in one call (handsonvlm.py:609-622): gather the last hidden
     row (even/odd de-interleave) and decode it -> [B,2,2] (the ``.squeeze(2)`` of handsonvlm.py:620)."""

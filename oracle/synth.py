@@ -136,6 +136,17 @@ def traj_cvae_state(token_dim: int, hidden: int = 512, latent: int = 256, in_dim
     return sd
 
 
+def traj_mlp_state(token_dim: int, hidden: int = 512, seed: int = 1) -> dict:
+    """State dict of ``MLPTrajDecoder(token_dim)`` (handsonvlm/model/language_model/traj_decoder.py:50-57 -> TrajMLP,
+    hoi_forecast/architecture/traj_decoder.py:94-104): ``hand_traj_decoder.mlp.{0,2,4}``."""
+    pre = "hand_traj_decoder.mlp."
+    sd = {}
+    for k, (o, i) in {"0": (hidden, token_dim), "2": (hidden, hidden), "4": (2, hidden)}.items():
+        sd[pre + k + ".weight"] = gen("trajmlp." + k + ".w", (o, i), 0.577 * i ** -0.5, seed)
+        sd[pre + k + ".bias"] = gen("trajmlp." + k + ".b", (o,), 0.577 * i ** -0.5, seed)
+    return sd
+
+
 def embed_table(D: int, vocab: int = VOCAB, seed: int = 1) -> torch.Tensor:
     """``embed_tokens = nn.Embedding(vocab, D)`` -- N(0,1) like nn.Embedding's default."""
     return gen("embed_tokens", (vocab, D), 1.0, seed)

@@ -225,6 +225,35 @@ def test_traj_head_step_full_size(D, B):
     assert torch.equal(raw, raw3)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-5), (torch.bfloat16, TOL_BF16)])
+def test_traj_mlp_decoder(dtype, tol):
+    """MLPTrajDecoder.inference (traj_decoder 'MLP'): three skinny linears, against the reference fixture (fp32, small) and
+    the fp32 oracle at the 7B width on bf16-rounded operands."""
+    from hvlm_b200.traj_decoder import MLPTrajDecoder
+    if dtype == torch.float32:
+        g = np.load("tests/golden/traj_mlp_infer.npz")
+        sd = synth.traj_mlp_state(32, seed=4)
+        dec = MLPTrajDecoder(token_dim=32)
+        dec.load_state_dict(sd, strict=True)
+        emb = synth.gen("trajmlp_emb", (3, 2, 4, 32), 1.0, seed=53)
+        out = dec.to(DEV).inference(pred_hand_embeddings=emb.to(DEV))
+        assert out.shape == (3, 2, 4, 2) and relmax(out, T(g["out"])) <= tol
+        return
+    Dc = 2048
+    sd = synth.traj_mlp_state(Dc, seed=7)
+    dec = MLPTrajDecoder(token_dim=Dc)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.to(DEV).to(dtype)
+    hl = synth.gen("trajmlp_hl", (2, 2 * Dc), 1.0, seed=8).to(dtype)
+    out = dec.inference_step(hl.to(DEV))
+    sd16 = {k: v.to(dtype).float() for k, v in sd.items()}
+    ref = restate.traj_mlp_inference(restate.gather_hand_traj_step(hl.float()), sd16).squeeze(2)
+    assert out.shape == (2, 2, 2) and out.dtype == dtype
+    assert relmax(out, ref) <= tol
+    with pytest.raises(NotImplementedError):
+        dec(pred_hand_embeddings=hl)
+
+
 def test_traj_head_many_rows_and_errors():
     dec, sd = _traj_module(64, 6, torch.float32)
     emb = synth.gen("traj_emb2", (5, 2, 3, 64), 1.0, seed=10)      # R = 30: several row chunks, ragged tail

@@ -68,6 +68,14 @@ def test_traj_step_matches_reference(golden):
     assert float((out - T(g["out"])).abs().max()) <= 1e-6
 
 
+def test_traj_mlp_inference_matches_reference(golden):
+    g = golden("traj_mlp_infer")
+    sd = synth.traj_mlp_state(32, seed=4)
+    emb = synth.gen("trajmlp_emb", (3, 2, 4, 32), 1.0, seed=53)
+    out = restate.traj_mlp_inference(emb, sd)
+    assert out.shape == (3, 2, 4, 2) and float((out - T(g["out"])).abs().max()) <= 1e-6
+
+
 # ------------------------------------------------------------------ gather (a7)
 @pytest.mark.parametrize("name,shape,seedname,seed", [
     ("gather_toy", None, None, None),
