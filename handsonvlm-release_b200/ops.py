@@ -156,6 +156,14 @@ linear.register_autograd(_linear_backward, setup_context=_linear_setup)
 # ------------------------------------------------------------------------------------------------
 # ViT-L/14 tower
 # ------------------------------------------------------------------------------------------------
+def _vit_workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    """Scratch for hvlm_vit_l14_fwd: the C side wants a 1024-byte aligned base (SWIZZLE_128B TMA tiles); the caching
+    allocator only promises 512, so over-allocate and slice."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
 @torch.library.custom_op("hvlm::vit_l14_hidden", mutates_args=())
 def vit_l14_hidden(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run: int) -> torch.Tensor:
     """pixels [N,3,224,224] -> residual stream f32 [N,257,1024] after n_layers_run layers."""
@@ -167,7 +175,7 @@ def vit_l14_hidden(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run
     N = pixels.shape[0]
     lib = L.lib()
     ws_bytes = lib.hvlm_vit_l14_workspace_bytes(N)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pixels.device)
+    ws = _vit_workspace(ws_bytes, pixels.device)
     hidden = torch.empty(N, 257, 1024, dtype=torch.float32, device=pixels.device)
     L.check(lib.hvlm_vit_l14_fwd(_p(weight_blob), n_layers_run, _p(pixels), _dt(pixels), N, _p(hidden), _p(ws),
                                  ws_bytes, _stream()), "hvlm_vit_l14_fwd")
@@ -190,7 +198,7 @@ def vit_l14_hidden_u8(weight_blob: torch.Tensor, frames: torch.Tensor, n_layers_
     N = frames.shape[0]
     lib = L.lib()
     ws_bytes = lib.hvlm_vit_l14_workspace_bytes(N)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=frames.device)
+    ws = _vit_workspace(ws_bytes, frames.device)
     hidden = torch.empty(N, 257, 1024, dtype=torch.float32, device=frames.device)
     mean = (C.c_float * 3)(*CLIP_MEAN)
     std = (C.c_float * 3)(*CLIP_STD)
