@@ -433,6 +433,23 @@ def stage_twostream():
         print(f"parts={parts}: median {sorted(reps)[2]:.3f} ms  ({' '.join(f'{r:.2f}' for r in reps)})  bit-identical={same}", flush=True)
 
 
+def stage_hf_eager():
+    """Context number: the reference's own GPU path for the tower -- HF CLIPVisionModel (24 layers, fp16/bf16 eager, SDPA,
+    output_hidden_states=True as clip_encoder.py:44 calls it) on the same 100-frame clip."""
+    import transformers
+    cfg = transformers.CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                                        num_attention_heads=16, image_size=224, patch_size=14, projection_dim=768)
+    for dt in (torch.float16, torch.bfloat16):
+        m = transformers.CLIPVisionModel(cfg).to(dev).to(dt).eval()
+        px = torch.randn(100, 3, 224, 224, device=dev, dtype=dt)
+        with torch.no_grad():
+            fn = lambda: m(px, output_hidden_states=True).hidden_states[-2][:, 1:]
+            ms = _time(fn, 10)
+        print(f"HF CLIPVisionModel eager {str(dt)[6:]} 100 frames: {ms:.2f} ms  {100 / ms * 1e3:.0f} frames/s", flush=True)
+        RES[f"hf_eager_{str(dt)[6:]}"] = ms
+        del m
+
+
 def stage_latency():
     """Small-batch tower latency (configs[0]: one image): stream launches vs one CUDA-graph replay."""
     import types as _t
