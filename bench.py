@@ -24,9 +24,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 import types
 import zlib
