@@ -186,6 +186,8 @@ class VisualToTokenHelper:
         n = out.shape[1]
         assert out.shape == torch.Size([self.b, n, self.token_dim]), \
             f"output_tokens.shape = {out.shape}, expected shape is {torch.Size([self.b, n, self.token_dim])}"
+        if kwargs.get("_hvlm_no_mask", False):        # internal: the splice treats a missing visual mask as all-True
+            return out, None
         attention_mask = torch.ones(self.b, n, dtype=torch.bool, device=out.device)
         return out, attention_mask
 
@@ -377,6 +379,37 @@ def gather_hand_traj_states(hidden_states: torch.Tensor, labels: torch.Tensor, h
     return out, valid
 
 
+class _LazyVisualEnd:
+    """``last_visual_token_index`` (handsonvlm.py:288) is a write-only side effect in the reference; evaluating it costs
+    three tiny kernels per call, so it is computed when somebody looks at it."""
+
+    def __init__(self, last_row_ids: torch.Tensor, n_visual: int):
+        self._ids, self._nv, self._val = last_row_ids, n_visual, None
+
+    def tensor(self) -> torch.Tensor:
+        if self._val is None:
+            self._val = (self._ids == IMAGE_TOKEN_INDEX).to(torch.int32).argmax() + self._nv
+            self._ids = None
+        return self._val
+
+    def item(self):
+        return self.tensor().item()
+
+    def __int__(self):
+        return int(self.item())
+
+    __index__ = __int__
+
+    def __eq__(self, other):
+        return int(self) == other
+
+    def __hash__(self):
+        return hash(int(self))
+
+    def __repr__(self):
+        return f"last_visual_token_index({int(self)})"
+
+
 class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
     """handsonvlm/model/handsonvlm_arch.py:8-17 + the released model's splice (handsonvlm.py:212-451)."""
 
@@ -394,7 +427,7 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
                                      video_compress_mode=self.config.video_compress_mode,
                                      mm_hidden_size=self.config.mm_hidden_size, token_dim=self.token_dim,
                                      cache_host=self)
-        visual_tokens, visual_mask = helper.pipeline(images=images, **kwargs)
+        visual_tokens, visual_mask = helper.pipeline(images=images, _hvlm_no_mask=True, **kwargs)
         assert visual_tokens.shape == torch.Size([self.B, visual_tokens.shape[1], self.token_dim]), visual_tokens.shape
         if getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False):
             # handsonvlm.py:263-286,343-344: <im_start>/<im_end> branch -- no hand embeddings on the tail, the <im_end>
@@ -407,8 +440,7 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
             self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None,
             kwargs.get("future_hands"), kwargs.get("is_evaluate", False))
         # side effect of the reference (handsonvlm.py:288): position right after the visual block
-        is_img = input_ids[-1] == IMAGE_TOKEN_INDEX
-        self.last_visual_token_index = is_img.to(torch.int32).argmax() + visual_tokens.shape[1]
+        self.last_visual_token_index = _LazyVisualEnd(input_ids[-1], visual_tokens.shape[1])
         return None, new_mask, past_key_values, embeds, new_labels
 
     def clear_visual_token_cache(self):
