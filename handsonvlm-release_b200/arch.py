@@ -36,9 +36,19 @@ _POOLED = ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temp
 
 def _project(projector, x2d: torch.Tensor) -> torch.Tensor:
     """mm_projector (nn.Linear 1024 -> D, with bias) on the tcgen05 GEMM; output in the projector's dtype."""
-    w = projector.weight
+    w, b = projector.weight, projector.bias
     out_f32 = w.dtype == torch.float32
-    y = ops.linear(x2d, w.to(torch.bfloat16), projector.bias.to(torch.float32), out_f32)
+    if torch.is_grad_enabled() and (w.requires_grad or b.requires_grad):
+        w16, b32 = w.to(torch.bfloat16), b.to(torch.float32)         # conversions stay in the autograd graph
+    else:
+        # inference: convert the parameters once per version instead of once per call
+        key = (w.data_ptr(), w._version, w.dtype, b.data_ptr(), b._version, b.dtype)
+        cached = getattr(projector, "_hvlm_gemm_params", None)
+        if cached is None or cached[0] != key:
+            cached = (key, w.detach().to(torch.bfloat16), b.detach().to(torch.float32))
+            projector._hvlm_gemm_params = cached
+        w16, b32 = cached[1], cached[2]
+    y = ops.linear(x2d, w16, b32, out_f32)
     return y if y.dtype == w.dtype else y.to(w.dtype)
 
 
