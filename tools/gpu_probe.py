@@ -450,6 +450,29 @@ def stage_hf_eager():
         del m
 
 
+def stage_stress():
+    """Race / nondeterminism hunt: many forwards of the same clip must be bit-identical (tower, pooled tokens, splice)."""
+    import types as _t
+    from hvlm_b200.tower import CLIPVisionTower
+    sd = synth.clip_state_dict(synth.VIT_L14, 0, "hf", n_layers=23)
+    tw = CLIPVisionTower("synthetic", _t.SimpleNamespace(mm_vision_select_layer=-2), delay_load=True)
+    tw.load_model(sd)
+    tw = tw.to(dev)
+    bad = 0
+    for n in (100, 37, 3):
+        px = torch.randn(n, 3, 224, 224, device=dev, dtype=torch.bfloat16)
+        ref = tw.forward_hidden(px).clone()
+        assert torch.isfinite(ref).all()
+        for i in range(40 if n == 100 else 100):
+            out = tw.forward_hidden(px)
+            if not torch.equal(out, ref):
+                bad += 1
+                print(f"MISMATCH n={n} iter={i} max|d|={(out - ref).abs().max().item():.3e}", flush=True)
+        print(f"n={n}: done, mismatches so far {bad}", flush=True)
+    RES["stress_mismatches"] = bad
+    print("stress mismatches:", bad, flush=True)
+
+
 def stage_latency():
     """Small-batch tower latency (configs[0]: one image): stream launches vs one CUDA-graph replay."""
     import types as _t
