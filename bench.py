@@ -381,7 +381,12 @@ def run_ours(args):
         flops = {"qkv_gemm": 2 * M * 3072 * 1024, "outproj_gemm": 2 * M * 1024 * 1024, "fc1_gemm": 2 * M * 4096 * 1024,
                  "fc2_gemm": 2 * M * 1024 * 4096, "patch_gemm": 2 * B * FRAMES * 256 * 1024 * 588,
                  "attention": B * FRAMES * 16 * 4 * 257 * 257 * 64}
-        bytes_ = {"layernorm": M * 1024 * (4 + 2), "pool": B * (FRAMES * 256 * 1024 * 4 + 356 * 1024 * 2),
+        from hvlm_b200 import arch as _arch
+        pool_bytes = B * (FRAMES * 256 * 1024 * 4 + 356 * 1024 * 2)                 # pool(hidden) -> bf16
+        if getattr(_arch, "_POOL_BEFORE_FC2", False):
+            # two pooling launches per step: hidden f32 -> f32 and f1 bf16 [.,4096] -> bf16 (fc2 runs on the pooled rows)
+            pool_bytes = B * (FRAMES * 256 * 1024 * 4 + 356 * 1024 * 4) + B * (FRAMES * 256 * 4096 * 2 + 356 * 4096 * 2)
+        bytes_ = {"layernorm": M * 1024 * (4 + 2), "pool": pool_bytes,
                   "splice": B * ((T_PROMPT - 1 + 356) * D * 2 + (T_PROMPT + 355) * (D * 2 + 9))}
         stages = {}
         for k, (t, n) in prof.items():
@@ -391,7 +396,8 @@ def run_ours(args):
                 st["tflops"] = round(flops[k] / avg_ms / 1e9, 1)
                 st["frac_of_sustained_peak"] = round(st["tflops"] / pk["tf_sustained"], 3)
             if k in bytes_:
-                per_launch = bytes_[k] / (1 if k != "splice" else 3)
+                # layernorm: bytes of one launch; pool / splice: bytes of one step spread over its launches (n // 2 per step)
+                per_launch = bytes_[k] if k == "layernorm" else bytes_[k] / max(n // 2, 1)
                 st["gbs"] = round(per_launch / avg_ms / 1e6, 1)
                 st["frac_of_hbm_peak"] = round(st["gbs"] / pk["hbm"], 3)
             stages[k] = st

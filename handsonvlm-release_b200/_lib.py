@@ -50,6 +50,7 @@ SIGNATURES = {
     "hvlm_vit_l14_workspace_bytes": (sz, [i32]),
     "hvlm_vit_l14_fwd": (i32, [p, i32, p, i32, i32, p, p, sz, p]),
     "hvlm_vit_l14_fwd_u8": (i32, [p, i32, p, C.POINTER(f32), C.POINTER(f32), i32, p, p, sz, p]),
+    "hvlm_vit_l14_fwd_open_mlp": (i32, [p, i32, p, i32, p, p, i32, p, p, sz, C.POINTER(C.c_uint64), p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
     "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, i32, p]),

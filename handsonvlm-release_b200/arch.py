@@ -21,6 +21,7 @@ returns every projected token, as its public signature requires.
 """
 from __future__ import annotations
 
+import os
 from abc import ABC, abstractmethod
 from typing import Optional
 
@@ -129,6 +130,36 @@ def distinct_frames(flat: torch.Tensor):
     return rep, inverse.to(torch.int32)
 
 
+# HVLM_POOL_BEFORE_FC2=0 runs the last layer's fc2 on every token row (A/B runs)
+_POOL_BEFORE_FC2 = os.environ.get("HVLM_POOL_BEFORE_FC2", "1") != "0"
+
+
+def _video_tokens_pool_before_fc2(tower, projector, flat, fmap, b, t, mode):
+    """The pooled video archs only need fixed averages over tokens of the tower's output, and the last thing the tower
+    does is linear (fc2 + bias + residual add), so it is applied AFTER pooling:
+        pool(h + f1 W2^T + b2) = pool(h) + pool(f1) W2^T + b2
+    fc2 then runs on the 356 pooled rows of a clip instead of its 25 700 token rows (same idea as pool-before-projector)."""
+    pm = L.POOL_MODES[mode]
+    with torch.no_grad():
+        hidden, f1 = tower.forward_hidden_open(flat)                # f32 [n,257,1024], bf16 [n,257,4096]
+        if fmap is not None and mode in ("temporal_spatial_pool", "spatial_pool", "temporal"):
+            p_h = ops.pool_slowfast_mapped(hidden, fmap, b, t, 257, 1, pm, False)
+            p_f = ops.pool_slowfast_mapped(f1, fmap, b, t, 257, 1, pm, True)
+        else:
+            if fmap is not None:
+                idx = fmap.to(torch.int64)
+                hidden, f1 = hidden.index_select(0, idx), f1.index_select(0, idx)
+            p_h = ops.pool_slowfast(hidden, b, t, 257, 1, pm, False)     # f32  [b,Nv,1024]
+            p_f = ops.pool_slowfast(f1, b, t, 257, 1, pm, True)          # bf16 [b,Nv,4096]
+        w2, b2 = tower.last_fc2()
+        n_out = p_h.shape[1]
+        p_h = p_h.reshape(-1, 1024)
+        ops.gemm(p_f.reshape(-1, 4096), w2, b2, epilogue="residual", resid=p_h, out=p_h)   # p_h += p_f W2^T + b2
+        pooled = p_h.to(torch.bfloat16)
+    tok = _project(projector, pooled)
+    return tok.reshape(b, n_out, -1)
+
+
 def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str, dedup: bool = False) -> torch.Tensor:
     """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project).  With ``dedup`` the tower only
     encodes the distinct frames of the batch and the pooling reads them through a frame map."""
@@ -141,6 +172,9 @@ def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: 
         if d is not None:
             rep, fmap = d
             flat = flat.index_select(0, rep)
+    if (mode in _POOLED and tower.select_feature == "patch" and tower.n_layers_needed >= 1 and _POOL_BEFORE_FC2
+            and hasattr(tower, "forward_hidden_open")):
+        return _video_tokens_pool_before_fc2(tower, projector, flat, fmap, b, t, mode)
     with torch.no_grad():
         hidden = tower.forward_hidden(flat)                         # f32 [n_distinct,257,1024]
     if mode in ("all", "none"):

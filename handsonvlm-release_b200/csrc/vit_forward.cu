@@ -102,7 +102,7 @@ extern "C" int hvlm_vit_qkv_gemm(const void* A, const void* w_qkv, const float* 
 
 static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
                             const float* u8_mean, const float* u8_std, int n_frames, float* hidden, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            size_t workspace_bytes, void* stream, bool open_last_mlp = false) {
     using namespace hvlm;
     if (!weight_blob || !pixels || !hidden || !workspace) return HVLM_ERR_BAD_ARG;
     if (n_frames <= 0 || n_layers_run < 0 || n_layers_run > HVLM_VIT_MAX_LAYERS) return HVLM_ERR_BAD_ARG;
@@ -205,6 +205,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + y.w_fc1, M, 4096, 1024, ep, s);
             if (rc) return rc;
         }
+        if (open_last_mlp && l + 1 == n_layers_run) break;   // the caller applies fc2 after pooling (it is linear)
         {
             EpiArgs ep;
             ep.bias = f32(y.b_fc2);
@@ -239,4 +240,24 @@ extern "C" int hvlm_vit_l14_fwd_u8(const void* weight_blob, int n_layers_run, co
         if (!(std_host[c] > 0.f)) return HVLM_ERR_BAD_ARG;
     return vit_l14_fwd_impl(weight_blob, n_layers_run, frames_nhwc, HVLM_F32, mean_host, std_host, n_frames, hidden,
                             workspace, workspace_bytes, stream);
+}
+
+// Same as hvlm_vit_l14_fwd / _fwd_u8 but the LAST layer's second MLP matmul is left to the caller: on return `hidden` is the
+// residual stream after the last attention block and workspace + *f1_offset holds gelu(fc1(LN2(hidden))) as bf16
+// [n_frames*257, 4096].  Token pooling is a fixed linear map over tokens, so the caller can pool both tensors first and
+// apply fc2 (+ bias + residual) to the 356 pooled rows per clip instead of the 25 700 token rows:
+//   pool(hidden + f1 W2^T + b2) = pool(hidden) + pool(f1) W2^T + b2.
+extern "C" int hvlm_vit_l14_fwd_open_mlp(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
+                                         const float* mean_host, const float* std_host, int n_frames, float* hidden,
+                                         void* workspace, size_t workspace_bytes, uint64_t* f1_offset, void* stream) {
+    if (!f1_offset || n_layers_run < 1) return HVLM_ERR_BAD_ARG;
+    const bool u8 = pix_dtype < 0;
+    if (u8) {
+        if (!mean_host || !std_host) return HVLM_ERR_BAD_ARG;
+        for (int c = 0; c < 3; ++c)
+            if (!(std_host[c] > 0.f)) return HVLM_ERR_BAD_ARG;
+    }
+    *f1_offset = hvlm::vit_workspace(n_frames > 0 ? n_frames : 1).f1;
+    return vit_l14_fwd_impl(weight_blob, n_layers_run, pixels, u8 ? HVLM_F32 : pix_dtype, u8 ? mean_host : nullptr,
+                            u8 ? std_host : nullptr, n_frames, hidden, workspace, workspace_bytes, stream, true);
 }

@@ -182,6 +182,36 @@ def vit_l14_hidden(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run
     return hidden
 
 
+def vit_l14_hidden_open(weight_blob: torch.Tensor, pixels: torch.Tensor, n_layers_run: int):
+    """Tower forward with the last layer's second MLP matmul left open (hvlm_vit_l14_fwd_open_mlp):
+    -> (hidden f32 [N,257,1024] after the last attention block, f1 bf16 [N,257,4096] = gelu(fc1(LN2(hidden)))).
+    ``pixels``: float [N,3,224,224] or raw uint8 [N,224,224,3].  Inference-only helper of the pooled token path; ``f1`` is
+    a view into the call's workspace."""
+    _need_cuda(weight_blob, pixels)
+    ensure_device()
+    u8 = pixels.dtype == torch.uint8
+    if u8:
+        if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (224, 224, 3):
+            raise ValueError(f"expected uint8 frames [N,224,224,3], got {tuple(pixels.shape)}")
+    elif pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, 224, 224):
+        raise ValueError(f"Input image size ({tuple(pixels.shape[-2:])}) doesn't match model (224*224).")
+    pixels = pixels.contiguous()
+    N = pixels.shape[0]
+    lib = L.lib()
+    ws_bytes = lib.hvlm_vit_l14_workspace_bytes(N)
+    ws = _vit_workspace(ws_bytes, pixels.device)
+    hidden = torch.empty(N, 257, 1024, dtype=torch.float32, device=pixels.device)
+    f1_off = C.c_uint64(0)
+    mean = (C.c_float * 3)(*CLIP_MEAN)
+    std = (C.c_float * 3)(*CLIP_STD)
+    L.check(lib.hvlm_vit_l14_fwd_open_mlp(_p(weight_blob), n_layers_run, _p(pixels), -1 if u8 else _dt(pixels), mean, std, N,
+                                          _p(hidden), _p(ws), ws_bytes, C.byref(f1_off), _stream()),
+            "hvlm_vit_l14_fwd_open_mlp")
+    o = int(f1_off.value)
+    f1 = ws[o:o + N * 257 * 4096 * 2].view(torch.bfloat16).view(N, 257, 4096)
+    return hidden, f1
+
+
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)    # OPENAI_CLIP_MEAN / STD (transformers CLIPImageProcessor defaults)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 

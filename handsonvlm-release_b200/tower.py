@@ -87,6 +87,23 @@ class CLIPVisionTower(nn.Module):
             images = images.float()
         return ops.vit_l14_hidden(self.weight_blob, images.to(self.device), self.n_layers_needed)
 
+    def forward_hidden_open(self, images: torch.Tensor):
+        """(hidden after the last attention block, f1 = gelu(fc1(LN2(hidden))) bf16 [N,257,4096]): the tower with the last
+        layer's fc2 left to the caller -- see ``last_fc2`` and ``arch.video_tokens``."""
+        if not self.is_loaded:
+            raise RuntimeError("CLIPVisionTower.load_model() has not been called")
+        if images.dtype not in (torch.uint8, torch.float32, torch.bfloat16, torch.float16):
+            images = images.float()
+        return ops.vit_l14_hidden_open(self.weight_blob, images.to(self.device), self.n_layers_needed)
+
+    def last_fc2(self):
+        """Views into the weight blob: (W2 bf16 [1024,4096], b2 f32 [1024]) of the last layer that runs."""
+        from .weights import vit_layout
+        y = vit_layout(self._blob_layers).layer[self.n_layers_needed - 1]
+        w = self.weight_blob[int(y.w_fc2): int(y.w_fc2) + 1024 * 4096 * 2].view(torch.bfloat16).view(1024, 4096)
+        b = self.weight_blob[int(y.b_fc2): int(y.b_fc2) + 1024 * 4].view(torch.float32)
+        return w, b
+
     @torch.no_grad()
     def forward(self, images):
         if type(images) is list:

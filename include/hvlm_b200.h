@@ -145,6 +145,14 @@ HVLM_API int hvlm_vit_l14_fwd(const void* weight_blob, int n_layers_run, const v
 HVLM_API int hvlm_vit_l14_fwd_u8(const void* weight_blob, int n_layers_run, const uint8_t* frames_nhwc,
                                  const float* mean_host, const float* std_host, int n_frames, float* hidden,
                                  void* workspace, size_t workspace_bytes, void* stream);
+/* The same forward with the LAST layer's second MLP matmul left to the caller (pix_dtype < 0: uint8 NHWC frames with
+ * mean_host / std_host, else an hvlm_dtype and the two pointers are ignored).  On return `hidden` is the residual stream
+ * after the last attention block and workspace + *f1_offset holds gelu(fc1(LN2(hidden))) as bf16 [n_frames*257, 4096].
+ * The LITA / HandsOnVLM token pooling (lita_arch.py:54-70, visual_to_tokens.py:252-271) is a fixed linear map over tokens,
+ * so  pool(hidden + f1 W2^T + b2) = pool(hidden) + pool(f1) W2^T + b2 : fc2 runs on the pooled rows only. */
+HVLM_API int hvlm_vit_l14_fwd_open_mlp(const void* weight_blob, int n_layers_run, const void* pixels, int pix_dtype,
+                              const float* mean_host, const float* std_host, int n_frames, float* hidden,
+                              void* workspace, size_t workspace_bytes, uint64_t* f1_offset, void* stream);
 /* hidden f32 [n,257,1024] -> feats [n,256,1024] (drop CLS) cast to out_dtype (clip_encoder.py:31-32,49). */
 HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls, void* stream);
 

@@ -754,6 +754,29 @@ def test_llava_list_of_image_groups_end_to_end(tower23):
     assert relmax(e2, re_) <= TOL_BF16
 
 
+@pytest.mark.parametrize("mode", ["temporal_spatial_pool", "temporal", "spatial_pool"])
+def test_pool_before_fc2_matches_full_tower(tower23, mode, monkeypatch):
+    """The last layer's fc2 applied after pooling (linearity) vs fc2 on every token row, then pooling: same tokens to
+    bf16 rounding, and both within the bar of the fp32 oracle."""
+    tw, sd = tower23("strong")
+    D, t, B = 4096, 5, 2
+    ps = synth.projector_state(D)
+    proj = torch.nn.Linear(1024, D)
+    proj.weight.data.copy_(ps["mm_projector.weight"])
+    proj.bias.data.copy_(ps["mm_projector.bias"])
+    proj = proj.to(DEV).to(torch.bfloat16)
+    px = synth.pixels((B, t, 3, 224, 224), seed=23)
+    with torch.no_grad():
+        monkeypatch.setattr(arch, "_POOL_BEFORE_FC2", True)
+        fast = arch.video_tokens(tw, proj, px.to(DEV).to(torch.bfloat16), mode)
+        monkeypatch.setattr(arch, "_POOL_BEFORE_FC2", False)
+        full = arch.video_tokens(tw, proj, px.to(DEV).to(torch.bfloat16), mode)
+    assert fast.shape == full.shape
+    assert relmax(fast, full) <= 8e-3
+    ref = restate.pipeline(px.to(torch.bfloat16).float(), sd, ps["mm_projector.weight"], ps["mm_projector.bias"], mode)[0]
+    assert relmax(fast, ref) <= TOL_BF16 and relmax(full, ref) <= TOL_BF16
+
+
 def test_lita_videos_to_tokens_archs(tower23):
     tw, sd = tower23("hf")
     D = 256
