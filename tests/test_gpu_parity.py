@@ -106,6 +106,34 @@ def test_pool_modes_vs_oracle(mode, dtype):
     assert relmax(ops.pool_tokens(tok.to(DEV), mode, torch.float32), ref) <= TOL_POOL
 
 
+def test_pool_and_gather_randomised_against_oracle():
+    """Seeded fuzz: pooling over odd frame counts (t < 4 duplicates the selected frames, lita_arch.py:54-58), channel
+    counts and modes; <hand_traj> gather with 0 or 4 hand tokens at random positions (incl. position 0 and the end)."""
+    rng = np.random.RandomState(99)
+    for case in range(12):
+        b = int(rng.randint(1, 4))
+        t = int(rng.choice([1, 2, 3, 4, 5, 9, 17]))
+        c = int(rng.choice([64, 320, 1024]))
+        mode = str(rng.choice(["temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temporal_spatial"]))
+        tok = synth.gen(f"fuzz.pool{case}", (b, t, 256, c), 1.0, case)
+        ref = restate.pool_tokens(tok, mode)
+        out = ops.pool_tokens(tok.to(DEV), mode, torch.float32)
+        assert out.shape == ref.shape and relmax(out, ref) <= TOL_POOL, (case, b, t, c, mode)
+    for case in range(20):
+        B = int(rng.randint(1, 6))
+        Lh = int(rng.randint(6, 90))
+        D = int(rng.choice([16, 64, 4096]))
+        hidden = synth.gen(f"fuzz.gh{case}", (B, Lh, D), 1.0, case).to(torch.bfloat16)
+        labels = torch.from_numpy(rng.randint(-100, 32000, size=(B, Lh))).long()
+        for bb in range(B):
+            if rng.rand() < 0.7:
+                pos = rng.choice(np.arange(1, Lh), size=4, replace=False)   # label[0] has no predictor row
+                labels[bb, torch.from_numpy(np.sort(pos)).long()] = 32100
+        out, valid, rows, counts = ops.hand_gather(hidden.to(DEV), labels.to(DEV), 32100)
+        ro, rv, rr = restate.gather_hand_traj(hidden, labels)
+        assert torch.equal(out.cpu(), ro) and torch.equal(valid.cpu(), rv) and torch.equal(rows.cpu(), rr), case
+
+
 def test_pool_reads_tower_layout_in_place():
     hid = synth.gen("hid", (6, 257, 1024), 1.0, 4)
     ref = restate.pool_tokens(hid[:, 1:].reshape(2, 3, 256, 1024), "temporal_spatial_pool")
