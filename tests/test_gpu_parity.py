@@ -54,6 +54,28 @@ def test_gemm_epilogues(M, N, K):
     assert relmax(r2, ref + res) <= 2e-5
 
 
+def test_gemm_randomised_shapes():
+    """Seeded fuzz of the tcgen05 GEMMs: ragged M (partial row blocks, single rows), every N class (128-multiples go to the
+    1-CTA kernel, 256-multiples to the 2-CTA kernel with whole / half-tile tails), K not a multiple of the 64-wide stage."""
+    rng = np.random.RandomState(7)
+    for case in range(24):
+        M = int(rng.choice([1, 2, 127, 128, 129, 255, 257, 300, 511, 777, 1025, 2311, 4099]))
+        N = int(rng.choice([128, 256, 384, 512, 768, 1024, 1280, 2048, 3072]))
+        K = int(rng.choice([8, 64, 72, 128, 200, 320, 640, 1024, 1096]))
+        a = synth.gen(f"fz.A{case}", (M, K), 1.0, case).to(torch.bfloat16).to(DEV)
+        w = synth.gen(f"fz.W{case}", (N, K), K ** -0.5, case).to(torch.bfloat16).to(DEV)
+        bias = synth.gen(f"fz.b{case}", (N,), 0.5, case).to(DEV)
+        res = synth.gen(f"fz.r{case}", (M, N), 1.0, case).to(DEV)
+        ref = a.float() @ w.float().t() + bias
+        tag = (case, M, N, K)
+        assert relmax(ops.gemm(a, w, bias, out_dtype=torch.float32), ref) <= 2e-5, tag
+        assert relmax(ops.gemm(a, w, bias, out_dtype=torch.bfloat16), ref) <= 5e-3, tag
+        assert relmax(ops.gemm(a, w, bias, epilogue="quick_gelu", out_dtype=torch.bfloat16), restate.quick_gelu(ref)) <= 6e-3, tag
+        r2 = res.clone()
+        ops.gemm(a, w, bias, epilogue="residual", resid=r2, out=r2)
+        assert relmax(r2, ref + res) <= 2e-5, tag
+
+
 def test_gemm_rejects_bad_arguments():
     a = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
     with pytest.raises(L.HvlmError):
