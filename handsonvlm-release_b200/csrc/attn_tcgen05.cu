@@ -569,7 +569,7 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
     }
     const int max_ctas = 2 * num_sms();
     const int grid = n_items < max_ctas ? n_items : max_ctas;
-    if (launch_pdl(attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1, static_cast<__nv_bfloat16*>(out), n_items,
+    if (launch_pdl_cls(2, attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1, static_cast<__nv_bfloat16*>(out), n_items,
                    trace) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;

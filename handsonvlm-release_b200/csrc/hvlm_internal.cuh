@@ -64,7 +64,7 @@ struct StageTimer {
 // runs its prologue (barrier init, TMEM alloc, descriptor prefetch) and then blocks in pdl_wait() until the
 // predecessor has completed and flushed.  Every kernel launched through this helper MUST call pdl_wait() before
 // touching global memory.  On for small batches, off for large ones, HVLM_PDL=1/0 overrides (policy and numbers in profile.cu).
-bool pdl_enabled();
+bool pdl_enabled(int cls = 1);   // cls: 0 = small streaming kernels (LayerNorm, im2col), 1 = GEMM, 2 = attention
 // RAII hint for the launches issued by the current host thread while it is alive (see profile.cu)
 struct PdlScope {
     explicit PdlScope(bool on);
@@ -72,7 +72,8 @@ struct PdlScope {
     int prev_;
 };
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+inline cudaError_t launch_pdl_cls(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                  Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -82,8 +83,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl_enabled(cls) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    return launch_pdl_cls(1, kernel, grid, block, smem, s, args...);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -19,17 +19,28 @@ struct Rec {
 static std::vector<Rec> g_recs;
 static std::vector<cudaEvent_t> g_free;
 
-// Programmatic dependent launch policy.  Measured on B200: for the 100-frame clip overlapping the ~3 us kernel prologues
-// does not pay (15.35 ms with PDL vs 15.20 ms without, same box), but for small batches the launch gaps and prologues are
-// a large share of every kernel: tower forward 1.91 -> 1.58 ms at 1 frame, 2.88 -> 2.53 ms at 10, 4.04 -> 3.76 ms at 20.
-// HVLM_PDL=1 / 0 forces it on / off; otherwise the caller's hint decides (vit_l14_fwd sets it for <= 32 frames).
+// Programmatic dependent launch policy.  Measured on B200, 100-frame clip, same box: PDL on every kernel is a loss
+// (15.35 vs 15.20 ms) and PDL on the LayerNorm / im2col launches alone is worse still (15.95-16.06 vs 15.67-15.76 ms: their
+// many small CTAs get scheduled early and sit in griddepcontrol.wait on slots the GEMM tail needs), but PDL on the GEMMs
+// alone wins 2 % (medians 15.03-15.21 vs 15.39-15.51 ms): their prologue (barrier init, TMEM alloc, descriptor prefetch)
+// overlaps the tail of the LayerNorm / attention kernel in front of them.  For small batches the launch gaps and
+// prologues are a large share of every kernel and PDL everywhere wins: tower forward 1.91 -> 1.58 ms at 1 frame,
+// 2.88 -> 2.53 ms at 10, 4.04 -> 3.76 ms at 20.
+// Policy: GEMMs always; everything when the caller's hint is set (vit_l14_fwd sets it for <= 32 frames).
+// HVLM_PDL=1 / 0 forces all on / off; HVLM_PDL_MASK selects classes for large batches (bit 0 LN/im2col, 1 GEMM, 2 attention).
 static thread_local int g_pdl_hint = 0;
-bool pdl_enabled() {
+bool pdl_enabled(int cls) {
     static const int forced = []() {
         const char* e = getenv("HVLM_PDL");
         return !e ? -1 : (e[0] == '1' ? 1 : 0);
     }();
-    return forced >= 0 ? forced == 1 : g_pdl_hint != 0;
+    // HVLM_PDL_MASK: per-class switch for large batches (bit 0 LayerNorm / im2col, bit 1 GEMM, bit 2 attention)
+    static const int mask = []() {
+        const char* e = getenv("HVLM_PDL_MASK");
+        return e ? atoi(e) : 2;      // default: GEMMs only
+    }();
+    if (forced >= 0) return forced == 1;
+    return g_pdl_hint != 0 || ((mask >> cls) & 1);
 }
 PdlScope::PdlScope(bool on) : prev_(g_pdl_hint) { g_pdl_hint = on ? 1 : 0; }
 PdlScope::~PdlScope() { g_pdl_hint = prev_; }

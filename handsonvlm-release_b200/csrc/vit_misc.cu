@@ -88,10 +88,10 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out, 
                      cudaStream_t s, int reverse, const float* add_rows, int add_period) {
     const int grid = (rows + 7) / 8;
     if (out_dtype == HVLM_F32)
-        launch_pdl(layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse, add_rows,
+        launch_pdl_cls(0, layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse, add_rows,
                    add_period);
     else if (out_dtype == HVLM_BF16)
-        launch_pdl(layernorm1024_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps,
+        launch_pdl_cls(0, layernorm1024_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps,
                    reverse, add_rows, add_period);
     else
         return HVLM_ERR_BAD_DTYPE;
@@ -222,7 +222,7 @@ int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv
         nrm.scale[c] = 1.0f / (255.0f * stdv[c]);
         nrm.shift[c] = -mean[c] / stdv[c];
     }
-    launch_pdl(im2col_u8_kernel, dim3(16, n_frames), dim3(256), 0, s, frames, static_cast<__nv_bfloat16*>(A), cls, pos, x0, nrm);
+    launch_pdl_cls(0, im2col_u8_kernel, dim3(16, n_frames), dim3(256), 0, s, frames, static_cast<__nv_bfloat16*>(A), cls, pos, x0, nrm);
     return check_last("im2col_u8");
 }
 
@@ -230,7 +230,7 @@ int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, cons
                   float* x0, cudaStream_t s) {
     dim3 grid(16, n_frames);
     HVLM_DISPATCH_DTYPE(pix_dtype, TT, {
-        launch_pdl(im2col_kernel<TT>, grid, dim3(256), 0, s, static_cast<const TT*>(pixels), static_cast<__nv_bfloat16*>(A), cls, pos, x0);
+        launch_pdl_cls(0, im2col_kernel<TT>, grid, dim3(256), 0, s, static_cast<const TT*>(pixels), static_cast<__nv_bfloat16*>(A), cls, pos, x0);
     });
     return check_last("im2col");
 }
