@@ -18,10 +18,14 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
                                                             const float* __restrict__ beta, TOut* __restrict__ out,
                                                             int rows, float eps, int reverse,
                                                             const float* __restrict__ add_rows, int add_period) {
-    pdl_launch_dependents();
+    // the dependent launch is triggered at the END of this kernel: its successor is a GEMM whose CTAs would otherwise become
+    // resident next to the LayerNorm CTAs right away (no shared memory to wait for) and halve their occupancy
     pdl_wait();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    if (row >= rows) {
+        pdl_launch_dependents();
+        return;
+    }
     if (reverse) row = rows - 1 - row;   // start with the rows the producer kernel touched last (still in L2)
     const int lane = threadIdx.x & 31;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * 1024);
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
             *reinterpret_cast<uint2*>(o) = w;
         }
     }
+    pdl_launch_dependents();
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
