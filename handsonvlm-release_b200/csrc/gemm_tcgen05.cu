@@ -6,7 +6,7 @@
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), fp32 accumulators in
 //     TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1
 //   * 4 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 32 columns), apply the epilogue
-//     (bias / quick-GELU / fp32 residual via TMA reduce-add / patch-embed + position embedding)
+//     (bias / quick-GELU / fp32 residual via TMA reduce-add / patch-embed rows behind each frame's CLS row)
 //     and store 128-bit vectors
 //   * persistent: grid = min(tiles, #SM); tiles are walked N-fastest so concurrently running CTAs share
 //     A rows and the (small, L2-resident) weight matrix

@@ -26,7 +26,7 @@ struct EpiArgs {
     const float* bias = nullptr;
     const float* resid = nullptr;
     void* out = nullptr;
-    const float* pos = nullptr;
+    const float* pos = nullptr;    // unused since the position embedding moved into the pre-LayerNorm kernel
     int reverse = 0;   // walk the tiles last-to-first (start with what the producer kernel left in L2)
     // fused LayerNorm of the updated residual rows (EPI_RESID_F32, N == 1024, 2-CTA kernel only): extra warps
     // normalise each 128-row block as soon as all of its column tiles have been reduced into `out`
