@@ -22,6 +22,7 @@ SPLICE_FLAG_IM_START_END = 0x100   # OR-able into the splice variant (include/hv
 EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PLAN_ERR_LEN_OVERFLOW, PLAN_ERR_IMG_OVERFLOW, PLAN_ERR_HAND_COUNT, PLAN_ERR_BAD_ID, PLAN_NOT_UNIFORM = 1, 2, 4, 8, 16
 VIT_MAX_LAYERS = 24
+ABI_VERSION = 2
 STAGES = ["im2col", "patch_gemm", "layernorm", "qkv_gemm", "attention", "outproj_gemm", "fc1_gemm", "fc2_gemm", "pool",
           "gemm", "splice", "gather", "other"]
 
@@ -60,8 +61,8 @@ SIGNATURES = {
     "hvlm_pool_slowfast_fwd_mapped": (i32, [p, i32, i64, p, p, i32, i32, i32, i32, i32, p]),
     "hvlm_pool_slowfast_bwd": (i32, [p, i32, p, i32, i32, i32, i32, i32, p]),
     "hvlm_splice_count": (i32, [p, i32, i32, p, p]),
-    "hvlm_splice_plan": (i32, [p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p]),
-    "hvlm_splice_plan_ragged": (i32, [p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p]),
+    "hvlm_splice_plan": (i32, [p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
+    "hvlm_splice_plan_ragged": (i32, [p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
     "hvlm_splice_fwd": (i32, [p, p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p]),
     "hvlm_splice_bwd": (i32, [p, i32, p, p, i32, i32, i32, i32, i32, p, p, p]),
     "hvlm_hand_gather_fwd": (i32, [p, i32, p, i64, i32, i32, i32, p, p, p, p, p]),
@@ -70,6 +71,11 @@ SIGNATURES = {
     "hvlm_traj_decode_workspace_bytes": (sz, [i32, i32]),
     "hvlm_traj_decode": (i32, [p, i64, i32, p, p, p, p, p, i32, i32, i32, i32, i32, p, p, sz, p]),
     "hvlm_skinny_linear": (i32, [p, i64, p, p, i32, i32, i32, i32, i32, p, p]),
+    "hvlm_frame_dedup_workspace_bytes": (sz, [i32]),
+    "hvlm_frame_dedup": (i32, [p, sz, i32, i32, p, p, p, p, sz, p]),
+    "hvlm_gather_rows": (i32, [p, sz, i32, p, i32, p, p]),
+    "hvlm_resize_table_host": (i32, [i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hvlm_resize_crop_u8": (i32, [p, i32, i32, i32, p, i32, i32, p, p, i32, p, p, i32, p]),
     "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
     "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
     "hvlm_launch_count": (C.c_uint64, []),
@@ -104,7 +110,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if L.hvlm_abi_version() != 1:
+    if L.hvlm_abi_version() != ABI_VERSION:
         raise RuntimeError("libhvlm_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -37,6 +37,9 @@ _POOLED = ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "temp
 
 def _project(projector, x2d: torch.Tensor) -> torch.Tensor:
     """mm_projector (nn.Linear 1024 -> D, with bias) on the tcgen05 GEMM; output in the projector's dtype."""
+    pre = getattr(projector, "_hvlm_pre_forward", None)
+    if pre is not None:
+        pre()          # e.g. dist.ProjectorGradReducer.wait: the ViT in front of this call did not need the projector
     w, b = projector.weight, projector.bias
     out_f32 = w.dtype == torch.float32
     if torch.is_grad_enabled() and (w.requires_grad or b.requires_grad):
@@ -57,35 +60,51 @@ class VisualTokenCache:
     """SURVEY.md section 8(f) item 1.  The reference re-runs the whole visual path for EVERY generated token
     (``generate(use_cache=False)``: handsonvlm_inference.py:99-109 -> handsonvlm.py:555-564, and HandsOnVLM dropped the
     ``T == 1`` early-out LLaVA has at llava_arch.py:117-120).  With ``config.hvlm_cache_visual_tokens = True`` the
-    drop-in keeps the visual tokens of the last clip and reuses them while the SAME image tensor (same storage, shape,
-    dtype and version counter, i.e. not modified in place) is passed again under ``torch.no_grad()``: the ViT, pooling
-    and projector then run once per sample instead of once per token.  Off by default (bit-identical either way)."""
+    drop-in keeps the visual tokens of the last clip and reuses them while the SAME image tensor object, not modified in
+    place since (version counter), is passed again under ``torch.no_grad()``: the ViT, pooling and projector then run once
+    per sample instead of once per token.  The cache holds a strong reference to that tensor, so its storage cannot be
+    freed and handed to the next sample's clip by the caching allocator while the entry is alive (an address-based key
+    would then serve stale tokens).  Off by default (bit-identical either way)."""
 
     def __init__(self):
+        self.images = None
         self.key = None
         self.value = None
         self.hits = 0
 
     @staticmethod
     def _key(images, extra):
-        return (images.data_ptr(), tuple(images.shape), images.dtype, images.device, images._version, extra)
+        return (images._version, tuple(images.shape), images.dtype, images.device, extra)
 
     def get(self, images, extra):
-        if torch.is_grad_enabled() or self.key is None or self.key != self._key(images, extra):
+        if torch.is_grad_enabled() or self.images is not images or self.key != self._key(images, extra):
             return None
         self.hits += 1
         return self.value
 
     def put(self, images, extra, value):
         if not torch.is_grad_enabled():
-            self.key, self.value = self._key(images, extra), value
+            self.images, self.key, self.value = images, self._key(images, extra), value
 
     def clear(self):
-        self.key = self.value = None
+        self.images = self.key = self.value = None
+
+
+def _dedup_setting(host, images):
+    """``config.hvlm_dedup_frames``: False | True (dynamic: one 4-byte readback) | int k >= 1 (static: at most k distinct
+    frames per clip, no host sync, violations reported by ``check_deferred_status``).  -> (enabled, capacity, deferred)"""
+    v = getattr(host.config, "hvlm_dedup_frames", False)
+    if v is True:
+        return True, 0, None
+    if not v:
+        return False, 0, None
+    d = _deferred(host, images.device)
+    d.poll()
+    return True, int(v) * images.shape[0], d
 
 
 def _cached_video_tokens(host, tower, projector, images, mode):
-    dedup = bool(getattr(host.config, "hvlm_dedup_frames", False))
+    dedup = _dedup_setting(host, images)
     if not getattr(host.config, "hvlm_cache_visual_tokens", False):
         return video_tokens(tower, projector, images, mode, dedup)
     cache = host.__dict__.setdefault("_hvlm_visual_cache", VisualTokenCache())
@@ -97,37 +116,89 @@ def _cached_video_tokens(host, tower, projector, images, mode):
     return tok
 
 
-_HASH_W = {}
+class DeferredChecks:
+    """Device-side status words that are looked at WITHOUT stalling the host: each check copies one int32 to pinned host
+    memory behind the kernel that produced it and records an event; ``poll`` (called at the start of the next static
+    splice / de-duplication) and ``flush`` (explicit, synchronising) raise for the completed ones.  This is how the
+    sync-free modes (``hvlm_static_splice``, ``hvlm_dedup_frames=<capacity>``) report a broken contract: one step late
+    instead of silently never."""
+
+    SLOTS = 64
+
+    def __init__(self, device):
+        self.host = torch.zeros(self.SLOTS, dtype=torch.int32).pin_memory()
+        self.pending = []          # (slot, event, raiser)
+        self.next = 0
+
+    def add(self, dev_word: torch.Tensor, raiser):
+        if len(self.pending) >= self.SLOTS:
+            self._finish(self.pending.pop(0), wait=True)
+        slot = self.next
+        self.next = (self.next + 1) % self.SLOTS
+        self.host[slot:slot + 1].copy_(dev_word.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((slot, ev, raiser))
+
+    def _finish(self, entry, wait):
+        slot, ev, raiser = entry
+        if wait:
+            ev.synchronize()
+        raiser(int(self.host[slot]))
+
+    def poll(self):
+        while self.pending and self.pending[0][1].query():
+            self._finish(self.pending.pop(0), wait=False)
+
+    def flush(self):
+        while self.pending:
+            self._finish(self.pending.pop(0), wait=True)
 
 
-def distinct_frames(flat: torch.Tensor):
-    """SURVEY 8(f).2 frame de-duplication.  flat [N, ...] -> (rep int64 [U], inverse int32 [N]) with
-    flat[rep[inverse[i]]] == flat[i] bit for bit, or None if every frame is distinct.  A 64-bit weighted checksum groups
-    candidate duplicates, an exact element-wise comparison confirms them (a checksum collision simply disables the
-    de-duplication); costs two streaming passes over the clip and ONE host sync."""
+def _deferred(host, device) -> DeferredChecks:
+    d = host.__dict__.get("_hvlm_deferred")
+    if d is None:
+        d = host.__dict__["_hvlm_deferred"] = DeferredChecks(device)
+    return d
+
+
+def check_deferred_status(host) -> None:
+    """Synchronise and raise if any sync-free call on ``host`` since the last check broke its contract (static splice:
+    not exactly one image token per sample / bad ids; static de-duplication: more distinct frames than the capacity)."""
+    d = host.__dict__.get("_hvlm_deferred")
+    if d is not None:
+        d.flush()
+
+
+def distinct_frames(flat: torch.Tensor, capacity: int = 0, deferred: Optional[DeferredChecks] = None):
+    """SURVEY 8(f).2 frame de-duplication on the device (``hvlm_frame_dedup``: checksum pass, byte-wise confirmation,
+    compaction -- three launches).  flat [N, ...] -> (distinct frames [U, ...], frame_map int32 [N]) with
+    ``distinct[frame_map[i]]`` bit-identical to ``flat[i]``, or None when every frame is distinct.
+    capacity == 0: U is read back (ONE 4-byte host sync).  capacity > 0 (a dataset contract: at most that many distinct
+    frames in the batch): no host sync at all -- the tower runs on exactly ``capacity`` rows and a broken contract is
+    reported through ``deferred``."""
     N = flat.shape[0]
-    rows = flat.reshape(N, -1)
-    nbytes = rows.shape[1] * rows.element_size()
-    if N < 2 or nbytes % 4 != 0:
+    nbytes = flat[0].numel() * flat.element_size()
+    if N < 2 or nbytes % 16 != 0:
         return None
-    words = rows.view(torch.int32)
-    key = (words.shape[1], flat.device)
-    w = _HASH_W.get(key)
-    if w is None:
-        g = torch.Generator(device="cpu").manual_seed(0x5EED)
-        w = torch.randint(-(2 ** 31), 2 ** 31 - 1, (words.shape[1],), generator=g, dtype=torch.int64).to(flat.device) | 1
-        _HASH_W[key] = w
-    h = (words.to(torch.int64) * w).sum(dim=1)                         # wrap-around int64 arithmetic
-    uniq, inverse = torch.unique(h, return_inverse=True)
-    U = uniq.numel()                                                  # host sync (size of a data-dependent result)
+    flat = flat.contiguous()
+    if capacity > 0:
+        cap = min(int(capacity), N)
+        if cap == N:
+            return None
+        fmap, rep, n_unique = ops.frame_dedup(flat, cap)
+        if deferred is not None:
+            def raiser(u, cap=cap):
+                if u > cap:
+                    raise RuntimeError(f"hvlm_dedup_frames={cap}: the batch had {u} distinct frames (static capacity "
+                                       "exceeded; its visual tokens were wrong)")
+            deferred.add(n_unique, raiser)
+        return ops.gather_rows(flat, rep, cap), fmap
+    fmap, rep, n_unique = ops.frame_dedup(flat)
+    U = int(n_unique.item())                                          # the one host sync of the dynamic mode
     if U == N:
         return None
-    rep = torch.full((U,), N, dtype=torch.int64, device=flat.device).scatter_reduce_(
-        0, inverse, torch.arange(N, device=flat.device), reduce="amin")
-    exact = bool((rows == rows[rep[inverse]]).all())                  # confirm: no checksum collision
-    if not exact:
-        return None
-    return rep, inverse.to(torch.int32)
+    return ops.gather_rows(flat, rep, U), fmap
 
 
 # HVLM_POOL_BEFORE_FC2=0 runs the last layer's fc2 on every token row (A/B runs)
@@ -160,18 +231,20 @@ def _video_tokens_pool_before_fc2(tower, projector, flat, fmap, b, t, mode):
     return tok.reshape(b, n_out, -1)
 
 
-def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str, dedup: bool = False) -> torch.Tensor:
-    """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project).  With ``dedup`` the tower only
-    encodes the distinct frames of the batch and the pooling reads them through a frame map."""
+def video_tokens(tower: CLIPVisionTower, projector, images: torch.Tensor, mode: str, dedup=False) -> torch.Tensor:
+    """images [b,t,3,224,224] -> visual tokens [b,Nv,D] (encode -> pool -> project).  With ``dedup`` (True, or the
+    (enabled, capacity, deferred) triple of ``_dedup_setting``) the tower only encodes the distinct frames of the batch and
+    the pooling reads them through a frame map."""
     assert images.ndim == 5, "multiple videos per sample not supported yet"
     b, t = images.shape[:2]
     flat = images.reshape(b * t, *images.shape[2:])      # [b*t,3,224,224] float, or raw uint8 [b*t,224,224,3]
     fmap = None
-    if dedup:
-        d = distinct_frames(flat)
+    if dedup is True:
+        dedup = (True, 0, None)
+    if dedup and dedup[0]:
+        d = distinct_frames(flat, dedup[1], dedup[2])
         if d is not None:
-            rep, fmap = d
-            flat = flat.index_select(0, rep)
+            flat, fmap = d
     if (mode in _POOLED and tower.select_feature == "patch" and tower.n_layers_needed >= 1 and _POOL_BEFORE_FC2
             and hasattr(tower, "forward_hidden_open")):
         return _video_tokens_pool_before_fc2(tower, projector, flat, fmap, b, t, mode)
@@ -252,7 +325,10 @@ class VisualToTokenHelper:
 # ------------------------------------------------------------------------------------------------
 # splice
 # ------------------------------------------------------------------------------------------------
-def _raise_on_status(bits: int):
+def _raise_on_status(bits: int, static: bool = False):
+    if static and bits & (L.PLAN_NOT_UNIFORM | L.PLAN_ERR_LEN_OVERFLOW):
+        raise RuntimeError("hvlm_static_splice contract violated: every sample must carry exactly one image token "
+                           "(hybrid_dataset.py:155-158); the previous batch's spliced outputs were wrong")
     if bits & L.PLAN_ERR_BAD_ID:
         raise IndexError("index out of range in self")                 # nn.Embedding's error for a bad token id
     if bits & L.PLAN_ERR_IMG_OVERFLOW:
@@ -265,7 +341,7 @@ def _raise_on_status(bits: int):
 
 
 def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual, visual_mask=None,
-                  future_hands=None, is_evaluate: bool = False, im_start_end: bool = False):
+                  future_hands=None, is_evaluate: bool = False, im_start_end: bool = False, last_visual_end=None):
     """Core of both prepare_inputs_labels_for_multimodal variants -> (attention_mask', embeds, labels').
     ``im_start_end``: the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch of llava_arch.py:146-161,172-181."""
     table = host.get_model().embed_tokens.weight
@@ -287,6 +363,8 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
     if visual.dtype != table.dtype:
         visual = visual.to(table.dtype)
     static = bool(getattr(host.config, "hvlm_static_splice", False)) and sizes is None
+    if static:
+        _deferred(host, input_ids.device).poll()                      # a broken contract of an EARLIER call raises here
     counts = ops.splice_count(input_ids)
     if static:
         # collator contract (hybrid_dataset.py:155-158): exactly one image token per sample, equal T
@@ -311,11 +389,14 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
         elif future_hands is not None:
             hand_mode, n_hand = 2, int(future_hands.shape[2])
     src_index, hand_code, lens_d, hand_scale, status = ops.splice_plan(
-        input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand, slot_offsets)
+        input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand, slot_offsets, last_visual_end)
     if not static:
         _raise_on_status(int(status.item()))
     else:
-        host._hvlm_splice_status = status                             # device flag; check lazily if wanted
+        # no host sync here: the status word is copied to pinned memory behind the plan kernel and looked at by the next
+        # static call's poll() or by check_deferred_status(host)
+        host._hvlm_splice_status = status
+        _deferred(host, input_ids.device).add(status, lambda bits: _raise_on_status(bits, static=True))
     embeds, new_labels, new_mask = ops.splice_gather(
         src_index, hand_code, lens_d, hand_scale, input_ids, labels, attention_mask, table, visual, visual_mask,
         future_hands if hand_mode else None, variant | (L.SPLICE_FLAG_IM_START_END if im_start_end else 0))
@@ -423,37 +504,6 @@ def gather_hand_traj_states(hidden_states: torch.Tensor, labels: torch.Tensor, h
     return out, valid
 
 
-class _LazyVisualEnd:
-    """``last_visual_token_index`` (handsonvlm.py:288) is a write-only side effect in the reference; evaluating it costs
-    three tiny kernels per call, so it is computed when somebody looks at it."""
-
-    def __init__(self, last_row_ids: torch.Tensor, n_visual: int):
-        self._ids, self._nv, self._val = last_row_ids, n_visual, None
-
-    def tensor(self) -> torch.Tensor:
-        if self._val is None:
-            self._val = (self._ids == IMAGE_TOKEN_INDEX).to(torch.int32).argmax() + self._nv
-            self._ids = None
-        return self._val
-
-    def item(self):
-        return self.tensor().item()
-
-    def __int__(self):
-        return int(self.item())
-
-    __index__ = __int__
-
-    def __eq__(self, other):
-        return int(self) == other
-
-    def __hash__(self):
-        return hash(int(self))
-
-    def __repr__(self):
-        return f"last_visual_token_index({int(self)})"
-
-
 class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
     """handsonvlm/model/handsonvlm_arch.py:8-17 + the released model's splice (handsonvlm.py:212-451)."""
 
@@ -480,11 +530,16 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
                 self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None, None, True,
                 im_start_end=True)
             return None, new_mask, past_key_values, embeds, new_labels
+        # side effect of the reference (handsonvlm.py:288): a 0-d int64 tensor, written by the plan kernel for the last
+        # image token of the last sample that has one (left at its previous value when no sample has an image token)
+        lve = self.__dict__.get("last_visual_token_index")
+        if not (isinstance(lve, torch.Tensor) and lve.dtype == torch.int64 and lve.dim() == 0
+                and lve.device == input_ids.device):
+            lve = torch.full((), -1, dtype=torch.int64, device=input_ids.device)
         new_mask, embeds, new_labels = splice_tokens(
             self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None,
-            kwargs.get("future_hands"), kwargs.get("is_evaluate", False))
-        # side effect of the reference (handsonvlm.py:288): position right after the visual block
-        self.last_visual_token_index = _LazyVisualEnd(input_ids[-1], visual_tokens.shape[1])
+            kwargs.get("future_hands"), kwargs.get("is_evaluate", False), last_visual_end=lve)
+        self.__dict__["last_visual_token_index"] = lve
         return None, new_mask, past_key_values, embeds, new_labels
 
     def clear_visual_token_cache(self):

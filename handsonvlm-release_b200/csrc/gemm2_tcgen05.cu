@@ -24,10 +24,14 @@ constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int BN = 256;          // columns per pair (each CTA loads 128 of them)
 constexpr int BK = 64;
 constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue (+ warps 6..9: 2nd epilogue group)
-template <int G>                 // G = number of 4-warp epilogue groups (each owns half of the tile's columns when G == 2)
+// G = number of 4-warp epilogue groups (each owns half of the tile's columns when G == 2)
+// RL = "residual load" epilogue: the fp32 residual tile is TMA-LOADED into the staging buffer, the accumulator is added
+//      in shared memory and the sum leaves with a plain TMA store (4 staging buffers: the load runs two units ahead)
+template <int G, bool RL = false>
 struct Cfg2 {
-    static constexpr int kStages = (G == 2) ? 5 : 6;
-    static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * 2 * (BM * 128) + 1024 + 256;
+    static constexpr int kStages = (G == 2 || RL) ? 5 : 6;
+    static constexpr int kBufs = RL ? 4 : 2;                     // staging buffers per epilogue group
+    static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * kBufs * (BM * 128) + 1024 + 256;
 };
 constexpr int kABytes = BM * BK * 2;            // 16 KB
 constexpr int kBBytes = (BN / 2) * BK * 2;      // 16 KB (this CTA's half of B)
@@ -166,26 +170,29 @@ struct Sched {
     }
 };
 
-template <int EPI, bool LN, int G>
+template <int EPI, bool LN, int G, bool RL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2) ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_bh, const __grid_constant__ CUtensorMap tma_c, int M, int N,
                      int K, EpiArgs ep, int split_tail) {
     static_assert(epi_is_staged<EPI>() || EPI == EPI_PATCH, "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
     static_assert(!(LN && G == 2), "the fused-LayerNorm warps and the second epilogue group use the same warp slots");
-    constexpr int kStages = Cfg2<G>::kStages;
+    static_assert(!RL || (EPI == EPI_RESID_F32 && !LN && G == 1), "residual-load epilogue: fp32 residual GEMM, one group");
+    constexpr int kStages = Cfg2<G, RL>::kStages;
+    constexpr int kBufs = Cfg2<G, RL>::kBufs;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * kABytes;
     uint8_t* smem_c = smem + kStages * kStageBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + G * 2 * kStoreBuf);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + G * kBufs * kStoreBuf);
     uint64_t* full_bar = bars;                       // [kStages]  TMA (both CTAs) -> MMA        (leader's copy is used)
     uint64_t* empty_bar = bars + kStages;            // [kStages]  MMA -> TMA                    (multicast to both)
     uint64_t* tfull_bar = bars + 2 * kStages;        // [2]        MMA -> epilogue               (multicast to both)
     uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogues of BOTH CTAs -> MMA (leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* ld_bar = bars + 2 * kStages + 5;       // [4]        RL only: residual tile landed in staging buffer i
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -211,6 +218,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 256 * G);   // 128*G epilogue threads in each CTA of the pair
         }
+        if constexpr (RL)
+            for (int i = 0; i < 4; ++i) mbar_init(&ld_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot);
@@ -304,10 +313,42 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const int row = q * 32 + lane;
         const int sw = row & 7;
         const bool store_warp = (((warp - 2) & 3) == 0);
-        uint8_t* smem_cg = smem_c + grp * 2 * kStoreBuf;
+        uint8_t* smem_cg = smem_c + grp * kBufs * kStoreBuf;
         const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;
         uint32_t ucount = 0;
         int pending_rb = -1;
+        // RL: the store warp walks the same (tile, unit) sequence two units AHEAD and TMA-loads the residual tiles
+        int pf_v = pair, pf_uu = 0, pf_units = 0, pf_m0 = 0, pf_ncol0 = 0;
+        auto pf_tile = [&]() {
+            if (pf_v < sched.nv) {
+                int m_blk, n_blk, half;
+                sched.decode(pf_v, m_blk, n_blk, half);
+                pf_m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+                pf_units = half < 0 ? kUnits : kUnits / 2;
+                pf_ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
+            }
+        };
+        auto pf_issue = [&](uint32_t g) {   // load the residual tile of the lookahead unit into buffer g & 3, advance
+            if (pf_v < sched.nv) {
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&ld_bar[g & 3u], kStoreBuf);
+                    tma_load_2d(smem_cg + (g & 3u) * kStoreBuf, &tma_c, &ld_bar[g & 3u], pf_ncol0 + pf_uu * kUnitCols, pf_m0);
+                }
+                __syncwarp();
+                if (++pf_uu == pf_units) {
+                    pf_uu = 0;
+                    pf_v += n_pairs;
+                    pf_tile();
+                }
+            }
+        };
+        if constexpr (RL) {
+            if (store_warp) {
+                pf_tile();
+                pf_issue(0);
+                pf_issue(1);
+            }
+        }
         for (int v = pair; v < sched.nv; v += n_pairs) {
             int m_blk, n_blk, half;
             sched.decode(v, m_blk, n_blk, half);
@@ -322,13 +363,23 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll 1
             for (int uu = 0; uu < units; ++uu, ++ucount) {
                 const int u = u0 + uu;
-                uint8_t* buf = smem_cg + (ucount & 1u) * kStoreBuf;
+                uint8_t* buf = smem_cg + (ucount & static_cast<uint32_t>(kBufs - 1)) * kStoreBuf;
                 uint8_t* brow = buf + row * 128;
-                if (store_warp) {
-                    if (elect_one()) bulk_wait_read<1>();
-                    __syncwarp();
+                if constexpr (RL) {
+                    if (store_warp) {
+                        // the store of unit ucount-2 has finished reading its buffer == buffer (ucount+2) & 3: refill it
+                        if (elect_one()) bulk_wait_read<1>();
+                        __syncwarp();
+                        pf_issue(ucount + 2u);
+                    }
+                    // no CTA barrier here: the load barrier below is what says "this buffer holds the residual tile"
+                } else {
+                    if (store_warp) {
+                        if (elect_one()) bulk_wait_read<1>();
+                        __syncwarp();
+                    }
+                    named_bar_sync(bar_a, 128);
                 }
-                named_bar_sync(bar_a, 128);
                 const int n0 = ncol0 + u * kUnitCols;
 #pragma unroll
                 for (int h = 0; h < kUnitCols / 32; ++h) {
@@ -337,7 +388,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     tmem_ld_wait();
                     float v[32];
                     epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
-                    if constexpr (kF32) {
+                    if constexpr (RL) {
+                        mbar_wait(&ld_bar[ucount & 3u], (ucount >> 2) & 1u);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4* p4 = reinterpret_cast<float4*>(brow + ((j ^ sw) << 4));
+                            float4 x = *p4;
+                            x.x += v[4 * j];
+                            x.y += v[4 * j + 1];
+                            x.z += v[4 * j + 2];
+                            x.w += v[4 * j + 3];
+                            *p4 = x;
+                        }
+                    } else if constexpr (kF32) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             *reinterpret_cast<float4*>(brow + ((j ^ sw) << 4)) =
@@ -364,7 +427,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 named_bar_sync(bar_b, 128);
                 if (store_warp) {
                     if (elect_one()) {
-                        if constexpr (EPI == EPI_RESID_F32) {
+                        if constexpr (RL) {
+                            tma_store_2d(&tma_c, buf, n0, m0);          // residual + acc + bias, summed in shared memory
+                        } else if constexpr (EPI == EPI_RESID_F32) {
                             tma_reduce_add_2d(&tma_c, buf, n0, m0);
                         } else if constexpr (EPI == EPI_PATCH) {
                             // hidden [frame][257][1024]: this CTA's 128 patch rows land behind the frame's CLS row
@@ -445,7 +510,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (warp == 1) tmem_dealloc_2sm(tmem_base);
 }
 
-template <int EPI, bool LN = false, int G = 1>
+template <int EPI, bool LN = false, int G = 1, bool RL = false>
 static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     CUtensorMap ta, tb, tbh, tc;
     {
@@ -493,8 +558,8 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         }
         if (rc) return rc;
     }
-    auto kern = gemm2_tcgen05_kernel<EPI, LN, G>;
-    constexpr int kSmemBytes = Cfg2<G>::kSmemBytes;
+    auto kern = gemm2_tcgen05_kernel<EPI, LN, G, RL>;
+    constexpr int kSmemBytes = Cfg2<G, RL>::kSmemBytes;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -535,6 +600,10 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
         const char* e = getenv("HVLM_GEMM_EPI_GROUPS");
         return !(e && e[0] == '1');
     }();
+    static const int resid_load_maxk = []() {
+        const char* e = getenv("HVLM_RESID_LOAD_MAXK");
+        return e ? atoi(e) : 1024;
+    }();
     if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
         return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
     switch (epi) {
@@ -548,6 +617,11 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
                 if (N != 1024 || !ep.ln_gamma || !ep.ln_beta || !ep.ln_count) return HVLM_ERR_BAD_ARG;
                 return launch_two<EPI_RESID_F32, true>(A, B, M, N, K, ep, s);
             }
+            // Short-K residual GEMMs (out_proj, K = 1024) are bound by their epilogue: the fp32 TMA reduce-add into the
+            // residual stream sustains ~7 B/clk/SM, twice the time of the K loop.  For K <= HVLM_RESID_LOAD_MAXK (default
+            // 1024; 0 disables) the epilogue TMA-loads the residual tile two units ahead, adds in shared memory and leaves
+            // with a plain TMA store.  Long-K GEMMs (fc2) hide the reduce-add behind the K loop and keep it.
+            if (K <= resid_load_maxk) return launch_two<EPI_RESID_F32, false, 1, true>(A, B, M, N, K, ep, s);
             return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
         case EPI_QKV_HM: return launch_two<EPI_QKV_HM>(A, B, M, N, K, ep, s);
         default: return HVLM_ERR_UNSUPPORTED;

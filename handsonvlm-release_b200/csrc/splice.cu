@@ -38,7 +38,8 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
                    const int32_t* __restrict__ slot_offsets /* NULL: every slot has Nv rows */, int B, int T, int Nv,
                    int n_img, int L, int vocab, int variant, int hand_mode, int n_hand_points,
                    int32_t* __restrict__ src_index, int8_t* __restrict__ hand_code, int32_t* __restrict__ lens,
-                   float* __restrict__ hand_scale, int32_t* __restrict__ status) {
+                   float* __restrict__ hand_scale, int32_t* __restrict__ status,
+                   int64_t* __restrict__ last_visual_end) {
     __shared__ int scan_smem[9];
     __shared__ int img_pos[kMaxImgPerSample];
     __shared__ int cum[kMaxImgPerSample + 1];   // cum[m] = rows added by the first m image tokens of this sample
@@ -69,7 +70,9 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     int len0 = T;
     for (int j = 0; j < min(counts[0], kMaxImgPerSample); ++j) len0 += nv_of(j) - 1;
     if (len > L) err |= HVLM_PLAN_ERR_LEN_OVERFLOW;
-    if (slot0 + max(k_img, 1) > n_img || k_img > kMaxImgPerSample) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
+    // a sample without image token advances cur_image_idx but never indexes the features (llava_arch.py:127-135,
+    // handsonvlm.py:234-245), so only samples that READ slots can overflow
+    if ((k_img > 0 && slot0 + k_img > n_img) || k_img > kMaxImgPerSample) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
     if (len != len0) err |= HVLM_PLAN_NOT_UNIFORM;
 
     // defaults: padding + no hand code
@@ -105,8 +108,9 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
         const int o0 = img_pos[j] + cum[j];
         const int g0 = slot_offsets ? (slot0 + j < n_img ? slot_offsets[slot0 + j] : 0) : (slot0 + j) * Nv;
         const int nv = nv_of(slot0 + j);
+        const bool slot_ok = slot0 + j < n_img;      // never plan a read past the visual tensor (error flagged above)
         for (int r = threadIdx.x; r < nv; r += blockDim.x)
-            if (o0 + r < L) dst[o0 + r] = -(1 + g0 + r);
+            if (o0 + r < L) dst[o0 + r] = slot_ok ? -(1 + g0 + r) : kPad;
     }
 
     // hand positional embedding codes: only the tail segment (text after the LAST image token) of samples
@@ -139,6 +143,18 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     if (threadIdx.x == 0) {
         lens[b] = len;
         if (hand_scale) hand_scale[b] = scale;
+        // handsonvlm.py:288 side effect: `self.last_visual_token_index = image_token_start + n_visual_tokens`, overwritten
+        // for every image token of every sample, where image_token_start indexes the ids that are LEFT after the previous
+        // image token was cut off.  The value that survives is the one of the last image token of the last sample that
+        // has one: only that sample's CTA writes.
+        if (last_visual_end && k_img > 0 && k_img <= kMaxImgPerSample) {
+            bool last = true;
+            for (int i = b + 1; i < B; ++i) last = last && counts[i] == 0;
+            if (last) {
+                const int rel = img_pos[k_img - 1] - (k_img > 1 ? img_pos[k_img - 2] + 1 : 0);
+                *last_visual_end = static_cast<int64_t>(rel) + nv_of(slot0 + k_img - 1);
+            }
+        }
     }
     if (err) atomicOr(status, err);
 }
@@ -267,7 +283,7 @@ extern "C" int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* coun
 static int splice_plan_impl(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B, int T, int Nv,
                             int n_img, int L, int vocab, int variant, int hand_mode, int n_hand_points,
                             int32_t* src_index, int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status,
-                            void* stream) {
+                            int64_t* last_visual_end, void* stream) {
     using namespace hvlm;
     if (!ids || !counts || !src_index || !hand_code || !lens || !status) return HVLM_ERR_BAD_ARG;
     if (B <= 0 || T <= 0 || Nv <= 0 || n_img <= 0 || L <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
@@ -277,24 +293,25 @@ static int splice_plan_impl(const int64_t* ids, const int32_t* counts, const int
     StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_plan_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, counts, slot_offsets, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index, hand_code,
-        lens, hand_scale, status);
+        lens, hand_scale, status, last_visual_end);
     return check_last("splice_plan");
 }
 
 extern "C" int hvlm_splice_plan(const int64_t* ids, const int32_t* counts, int B, int T, int Nv, int n_img, int L,
                                 int vocab, int variant, int hand_mode, int n_hand_points, int32_t* src_index,
-                                int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status, void* stream) {
+                                int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status,
+                                int64_t* last_visual_end, void* stream) {
     return splice_plan_impl(ids, counts, nullptr, B, T, Nv, n_img, L, vocab, variant, hand_mode, n_hand_points, src_index,
-                            hand_code, lens, hand_scale, status, stream);
+                            hand_code, lens, hand_scale, status, last_visual_end, stream);
 }
 
 extern "C" int hvlm_splice_plan_ragged(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B,
                                        int T, int n_slots, int L, int vocab, int variant, int hand_mode,
                                        int n_hand_points, int32_t* src_index, int8_t* hand_code, int32_t* lens,
-                                       float* hand_scale, int32_t* status, void* stream) {
+                                       float* hand_scale, int32_t* status, int64_t* last_visual_end, void* stream) {
     if (!slot_offsets) return HVLM_ERR_BAD_ARG;
     return splice_plan_impl(ids, counts, slot_offsets, B, T, 1, n_slots, L, vocab, variant, hand_mode, n_hand_points,
-                            src_index, hand_code, lens, hand_scale, status, stream);
+                            src_index, hand_code, lens, hand_scale, status, last_visual_end, stream);
 }
 
 extern "C" int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens,

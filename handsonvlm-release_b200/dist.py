@@ -39,15 +39,29 @@ def shard_clips(n_clips: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_clips, world))
 
 
+def _flat_sizes(projector):
+    nW = projector.weight.numel()
+    nb = projector.bias.numel() if getattr(projector, "bias", None) is not None else 0
+    return nW, nb
+
+
 def allreduce_projector_grads(projector: torch.nn.Module, group=None, async_op: bool = False):
-    """Mean all-reduce of the projector gradients as ONE flat fp32 bucket (a single latency-bound collective
-    instead of two).  Returns the work handle when async_op=True (call ``finish`` on it)."""
+    """Mean all-reduce of the projector gradients as ONE flat fp32 bucket of FIXED size ``weight.numel() + bias.numel()``
+    (a single latency-bound collective instead of two).  Every rank of the group issues the same collective every time:
+    a missing gradient (text-only micro-batch) contributes zeros and is created by the reduction, so ranks can never
+    disagree on the size of, or skip, the call.  Returns a ``finish`` callable when async_op=True.
+    Simple synchronous entry; the training loop uses :class:`ProjectorGradReducer` (preallocated bucket, overlap)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
-    grads = [p.grad for p in (projector.weight, projector.bias) if p.grad is not None]
-    if not grads:
-        return None
-    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    params = [projector.weight] + ([projector.bias] if getattr(projector, "bias", None) is not None else [])
+    nW, nb = _flat_sizes(projector)
+    dev = projector.weight.device
+    flat = torch.zeros(nW + nb, dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        if p.grad is not None:
+            flat[off: off + p.numel()].copy_(p.grad.reshape(-1))
+        off += p.numel()
     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     def finish():
@@ -55,15 +69,140 @@ def allreduce_projector_grads(projector: torch.nn.Module, group=None, async_op: 
             work.wait()
         flat.div_(dist.get_world_size(group))
         off = 0
-        for g in grads:
-            n = g.numel()
-            g.copy_(flat[off: off + n].reshape(g.shape).to(g.dtype))
+        for p in params:
+            n = p.numel()
+            g = flat[off: off + n].reshape(p.shape)
+            if p.grad is None:
+                p.grad = g.to(p.dtype)
+            else:
+                p.grad.copy_(g)
             off += n
 
     if async_op:
         return finish
     finish()
     return None
+
+
+class ProjectorGradReducer:
+    """The training-shaped variant's only exchange step (the reference leaves it to ZeRO's reduce,
+    scripts/zero3.json:16-27): mean all-reduce of ``mm_projector.{weight,bias}.grad`` over NCCL / NVLink.
+
+    * ONE flat fp32 bucket ``[D*1024 + D]`` allocated once.  With ``use_sink=True`` the wgrad GEMM and the bias column
+      sum of ``hvlm::linear``'s backward write their fp32 results STRAIGHT into it (``ops.register_wgrad_sink``): no
+      ``cat``, no packing pass.  (Gradient accumulation over several backwards per reduction needs ``use_sink=False``:
+      the bucket is then packed from ``.grad``.)
+    * ``reduce_async()`` right after ``backward()``: the collective is enqueued on a side stream behind the backward
+      kernels (``ReduceOp.AVG`` on NCCL: no separate division pass) and the call returns immediately.
+    * ``wait()`` before the gradients are consumed (optimizer step): the current stream waits for the collective and the
+      reduced values are cast into ``.grad``.  The vision tower is frozen, so the NEXT step's ViT forward does not depend
+      on the projector update and may be enqueued before ``wait()`` -- ``arch`` calls ``projector._hvlm_pre_forward()``
+      right before the projector GEMM, which is where :meth:`attach` hooks the wait (+ an optional update callback).
+    Every rank issues exactly one fixed-size collective per ``reduce_async`` call, whatever gradients it has."""
+
+    def __init__(self, projector: torch.nn.Module, group=None, use_sink: bool = True):
+        self.projector = projector
+        self.group = group
+        self.params = [projector.weight] + ([projector.bias] if getattr(projector, "bias", None) is not None else [])
+        self.nW, self.nb = _flat_sizes(projector)
+        dev = projector.weight.device
+        self.bucket = torch.zeros(self.nW + self.nb, dtype=torch.float32, device=dev)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.backend = dist.get_backend(group) if dist.is_initialized() else None
+        self.stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.pending = None       # (work handle | None, done event | None)
+        self.use_sink = use_sink and dev.type == "cuda"
+        self.on_reduced = None    # optional callback run by wait() after the gradients are in place (optimizer step)
+        self.last_ms = None
+        self._ev = None
+        if self.use_sink:
+            from . import ops
+            ops.register_wgrad_sink(tuple(projector.weight.shape), dev, self.bucket[: self.nW].view(projector.weight.shape),
+                                    self.bucket[self.nW:] if self.nb else None)
+
+    def close(self):
+        if self.use_sink:
+            from . import ops
+            ops.unregister_wgrad_sink(tuple(self.projector.weight.shape), self.projector.weight.device)
+        if getattr(self.projector, "_hvlm_pre_forward", None) == self.wait:
+            self.projector._hvlm_pre_forward = None
+
+    def attach(self, on_reduced=None):
+        """Defer ``wait()`` to the moment the projector is next used (see class docstring)."""
+        self.on_reduced = on_reduced
+        self.projector._hvlm_pre_forward = self.wait
+        return self
+
+    def _pack(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.bucket[off: off + n].zero_()
+            else:
+                self.bucket[off: off + n].copy_(p.grad.reshape(-1))
+            off += n
+
+    def reduce_async(self, timed: bool = False):
+        if self.pending is not None:
+            self.wait()
+        if not self.use_sink:
+            self._pack()
+        elif any(p.grad is None for p in self.params):
+            self._pack()                      # no backward reached the projector on this rank: contribute zeros
+        if self.world == 1:
+            self.pending = (None, None, None)
+            return
+        if self.stream is None:               # gloo / CPU
+            work = dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.pending = (work, None, None)
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            e0 = e1 = None
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            op = dist.ReduceOp.AVG if self.backend == "nccl" else dist.ReduceOp.SUM
+            dist.all_reduce(self.bucket, op=op, group=self.group)
+            if op != dist.ReduceOp.AVG:
+                self.bucket.div_(self.world)
+            if timed:
+                e1.record()
+            done = torch.cuda.Event()
+            done.record()
+        self.pending = (None, done, (e0, e1) if timed else None)
+
+    def wait(self):
+        if self.pending is None:
+            return
+        work, done, tim = self.pending
+        self.pending = None
+        if work is not None:
+            work.wait()
+            self.bucket.div_(self.world)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+        self._ev = tim
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            g = self.bucket[off: off + n].view(p.shape)
+            if p.grad is None:
+                p.grad = g.to(p.dtype)
+            else:
+                p.grad.copy_(g)
+            off += n
+        if self.on_reduced is not None:
+            self.on_reduced()
+
+    def last_allreduce_ms(self):
+        """Device time of the last timed collective (CUDA events on the side stream); synchronises."""
+        if self._ev is None:
+            return None
+        e0, e1 = self._ev
+        e1.synchronize()
+        return e0.elapsed_time(e1)
 
 
 def max_over_ranks(value: float, device=None) -> float:

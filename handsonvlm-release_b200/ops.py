@@ -113,6 +113,20 @@ def _(x, w_bf16, bias_f32, out_f32):
     return x.new_empty(x.shape[0], w_bf16.shape[0], dtype=torch.float32 if out_f32 else torch.bfloat16)
 
 
+# (weight shape, device) -> (dW fp32 [N,K], db fp32 [N] | None): where the projector wgrad / bias grad are written when a
+# dist.ProjectorGradReducer owns a flat all-reduce bucket (the collective then reads what the kernels wrote, no packing)
+_wgrad_sinks: dict = {}
+
+
+def register_wgrad_sink(weight_shape, device, dW: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    assert dW.dtype == torch.float32 and tuple(dW.shape) == tuple(weight_shape) and dW.is_contiguous()
+    _wgrad_sinks[(tuple(weight_shape), torch.device(device))] = (dW, db)
+
+
+def unregister_wgrad_sink(weight_shape, device) -> None:
+    _wgrad_sinks.pop((tuple(weight_shape), torch.device(device)), None)
+
+
 @torch.library.custom_op("hvlm::linear_bwd", mutates_args=())
 def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w_bf16: torch.Tensor, need_dx: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """dW [N,K] f32 = dY^T X, db [N] f32 = colsum(dY), dX [M,K] f32 = dY W (only if need_dx)."""
@@ -120,8 +134,20 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, w_bf16: torch.Tensor, need_dx:
     K = x.shape[1]
     dyT = transpose_to_bf16(dy)                  # [N, Mp]   A operand, K-major over tokens
     xT = transpose_to_bf16(x)                    # [K, Mp]   B operand
-    dW = gemm(dyT, xT, None, out_dtype=torch.float32)
-    db = colsum(dy)
+    sink = _wgrad_sinks.get(((N, K), dy.device))
+    if sink is not None:
+        # results land in the reducer's flat bucket; autograd gets the bf16 cast it would make anyway (custom-op outputs
+        # must not alias the sink)
+        gemm(dyT, xT, None, out_dtype=torch.float32, out=sink[0])
+        dW = sink[0].to(torch.bfloat16)
+        if sink[1] is not None:
+            L.check(L.lib().hvlm_colsum(_p(dy.contiguous()), _dt(dy), _p(sink[1]), M, N, _stream()), "hvlm_colsum")
+            db = sink[1].clone()
+        else:
+            db = colsum(dy)
+    else:
+        dW = gemm(dyT, xT, None, out_dtype=torch.float32)
+        db = colsum(dy)
     if need_dx:
         wT = transpose_to_bf16(w_bf16)           # [K, N]
         dyb = dy if dy.dtype == torch.bfloat16 else dy.to(torch.bfloat16)
@@ -412,9 +438,13 @@ def splice_count(ids: torch.Tensor) -> torch.Tensor:
 
 
 def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lout: int, vocab: int, variant: int,
-                hand_mode: int, n_hand: int, slot_offsets: Optional[torch.Tensor] = None):
+                hand_mode: int, n_hand: int, slot_offsets: Optional[torch.Tensor] = None,
+                last_visual_end: Optional[torch.Tensor] = None):
     """``slot_offsets`` (int32 [n_img+1], device): per-slot row ranges of a row-concatenated visual tensor, for visual
-    token blocks of different lengths (``Nv`` is ignored then)."""
+    token blocks of different lengths (``Nv`` is ignored then).  ``last_visual_end``: optional 0-d int64 device tensor
+    that receives the reference's ``last_visual_token_index`` (handsonvlm.py:288)."""
+    if last_visual_end is not None:
+        assert last_visual_end.dtype == torch.int64 and last_visual_end.numel() == 1 and last_visual_end.is_cuda
     ids = ids.contiguous()
     B, T = ids.shape
     dev = ids.device
@@ -427,11 +457,12 @@ def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lo
         assert slot_offsets.dtype == torch.int32 and slot_offsets.numel() == n_img + 1 and slot_offsets.is_cuda
         L.check(L.lib().hvlm_splice_plan_ragged(_p(ids), _p(counts), _p(slot_offsets.contiguous()), B, T, n_img, Lout,
                                                 vocab, variant, hand_mode, n_hand, _p(src_index), _p(hand_code),
-                                                _p(lens), _p(hand_scale), _p(status), _stream()),
+                                                _p(lens), _p(hand_scale), _p(status), _p(last_visual_end), _stream()),
                 "hvlm_splice_plan_ragged")
         return src_index, hand_code, lens, hand_scale, status
     L.check(L.lib().hvlm_splice_plan(_p(ids), _p(counts), B, T, Nv, n_img, Lout, vocab, variant, hand_mode, n_hand,
-                                     _p(src_index), _p(hand_code), _p(lens), _p(hand_scale), _p(status), _stream()),
+                                     _p(src_index), _p(hand_code), _p(lens), _p(hand_scale), _p(status),
+                                     _p(last_visual_end), _stream()),
             "hvlm_splice_plan")
     return src_index, hand_code, lens, hand_scale, status
 
@@ -666,4 +697,90 @@ def hand_gather_step(hidden_last: torch.Tensor) -> torch.Tensor:
     out = torch.empty(B, 2, 1, D // 2, dtype=hidden_last.dtype, device=hidden_last.device)
     L.check(L.lib().hvlm_hand_gather_step(_p(hidden_last), _dt(hidden_last), B, D, _p(out), _stream()),
             "hvlm_hand_gather_step")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# frame de-duplication and the uint8 resize / centre crop in front of the tower
+# ------------------------------------------------------------------------------------------------
+def frame_dedup(frames: torch.Tensor, capacity: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """frames [N, ...] (any dtype, contiguous; bytes per frame % 16 == 0) -> (frame_map int32 [N], rep int32 [N],
+    n_unique int32 [1]), all on the device, no host sync.  ``rep[:n_unique]`` lists the first occurrence of every distinct
+    frame (padded with 0), ``frame_map[i]`` is frame i's index in that list."""
+    _need_cuda(frames)
+    ensure_device()
+    frames = frames.contiguous()
+    N = frames.shape[0]
+    fb = frames[0].numel() * frames.element_size()
+    dev = frames.device
+    frame_map = torch.empty(N, dtype=torch.int32, device=dev)
+    rep = torch.empty(N, dtype=torch.int32, device=dev)
+    n_unique = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = L.lib()
+    need = int(lib.hvlm_frame_dedup_workspace_bytes(N))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    L.check(lib.hvlm_frame_dedup(_p(frames), fb, N, int(capacity), _p(frame_map), _p(rep), _p(n_unique), _p(ws), need, _stream()),
+            "hvlm_frame_dedup")
+    return frame_map, rep, n_unique
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, n_out: Optional[int] = None) -> torch.Tensor:
+    """out[i] = src[idx[i]] for i < n_out (idx int32 on the device; n_out is a HOST number, default len(idx))."""
+    _need_cuda(src, idx)
+    ensure_device()
+    src = src.contiguous()
+    assert idx.dtype == torch.int32 and idx.is_contiguous()
+    n_out = idx.numel() if n_out is None else n_out
+    assert 0 < n_out <= idx.numel()
+    rb = src[0].numel() * src.element_size()
+    out = torch.empty((n_out,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    L.check(L.lib().hvlm_gather_rows(_p(src), rb, src.shape[0], _p(idx), n_out, _p(out), _stream()), "hvlm_gather_rows")
+    return out
+
+
+_resize_tables: dict = {}
+
+
+def resize_tables(in_size: int, out_size: int, crop0: int, crop_n: int, device) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Pillow bicubic coefficient table of one axis (hvlm_resize_table_host), cached on the device per geometry."""
+    key = (in_size, out_size, crop0, crop_n, str(device))
+    hit = _resize_tables.get(key)
+    if hit is None:
+        lib = L.lib()
+        k = lib.hvlm_resize_table_host(in_size, out_size, crop0, crop_n, None, None)
+        if k <= 0:
+            raise L.HvlmError("hvlm_resize_table_host", k)
+        bounds = (C.c_int32 * (2 * crop_n))()
+        coef = (C.c_int32 * (crop_n * k))()
+        rc = lib.hvlm_resize_table_host(in_size, out_size, crop0, crop_n, bounds, coef)
+        if rc != k:
+            raise L.HvlmError("hvlm_resize_table_host", rc)
+        hit = (torch.tensor(list(bounds), dtype=torch.int32).to(device), torch.tensor(list(coef), dtype=torch.int32).to(device), k)
+        _resize_tables[key] = hit
+    return hit
+
+
+def clip_resize_output_size(h: int, w: int, shortest: int = 224) -> Tuple[int, int]:
+    """transformers get_resize_output_image_size(size=int, default_to_square=False): (new_h, new_w)."""
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = shortest, int(shortest * long / short)
+    return (new_long, new_short) if w <= h else (new_short, new_long)
+
+
+def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor:
+    """Decoded frames uint8 [N,H,W,3] -> uint8 [N,size,size,3]: CLIPImageProcessor's resize (shortest edge -> size, PIL
+    BICUBIC, bit-identical to Pillow) + centre crop, one launch; feed the result to the tower's uint8 path."""
+    _need_cuda(frames)
+    ensure_device()
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError(f"expected uint8 frames [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
+    frames = frames.contiguous()
+    N, H, W, _ = frames.shape
+    nh, nw = clip_resize_output_size(H, W, size)
+    top, left = (nh - size) // 2, (nw - size) // 2
+    xb, xc, xk = resize_tables(W, nw, left, size, frames.device)
+    yb, yc, yk = resize_tables(H, nh, top, size, frames.device)
+    out = torch.empty(N, size, size, 3, dtype=torch.uint8, device=frames.device)
+    L.check(L.lib().hvlm_resize_crop_u8(_p(frames), N, H, W, _p(out), size, size, _p(xb), _p(xc), xk, _p(yb), _p(yc), yk,
+                                        _stream()), "hvlm_resize_crop_u8")
     return out

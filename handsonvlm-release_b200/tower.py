@@ -30,6 +30,21 @@ def _load_clip_state_dict(src: str) -> dict:
     return CLIPVisionModel.from_pretrained(src).state_dict()
 
 
+def _default_image_processor(src=None):
+    """The reference reads ``vision_tower.image_processor`` (handsonvlm/model/builder.py:109, handsonvlm/train/train.py:318),
+    set by ``CLIPImageProcessor.from_pretrained(name)`` in load_model (clip_encoder.py:23).  Prefer the PIL-backed processor
+    (what transformers==4.31.0, the reference's pin, runs); fall back to the CLIP defaults (shortest edge 224, bicubic,
+    centre crop 224, OPENAI_CLIP mean / std) when ``src`` has no preprocessor_config.json or there is no network."""
+    import transformers
+    cls = getattr(transformers.models.clip, "CLIPImageProcessorPil", None) or transformers.CLIPImageProcessor
+    if isinstance(src, str):
+        try:
+            return cls.from_pretrained(src)
+        except Exception:
+            pass
+    return cls()
+
+
 class CLIPVisionTower(nn.Module):
     def __init__(self, vision_tower="openai/clip-vit-large-patch14", args=None, delay_load=False):
         super().__init__()
@@ -38,10 +53,14 @@ class CLIPVisionTower(nn.Module):
         self.select_layer = getattr(args, "mm_vision_select_layer", -2)
         self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
         self.cfg_only = types.SimpleNamespace(**_CFG)
-        self._dtype = torch.bfloat16
+        # what `.dtype` reports: the reference returns the HF module's parameter dtype (clip_encoder.py:57-59), fp32 after
+        # from_pretrained and whatever the caller's `.to(dtype=...)` / `.half()` set afterwards.  The kernels' numeric
+        # regime does not depend on it (bf16 operands, fp32 accumulation / residual stream).
+        # It is tracked by an empty floating-point buffer that nn.Module's own machinery casts along with the module.
+        self.register_buffer("_dtype_probe", torch.zeros(0, dtype=torch.float32), persistent=False)
         self.register_buffer("weight_blob", torch.zeros(0, dtype=torch.uint8), persistent=False)
-        if not delay_load and isinstance(vision_tower, dict):
-            self.load_model(vision_tower)
+        if not delay_load:
+            self.load_model(vision_tower if isinstance(vision_tower, dict) else None)
 
     # -- loading -------------------------------------------------------------------------------
     def load_model(self, state_dict=None):
@@ -51,6 +70,7 @@ class CLIPVisionTower(nn.Module):
         ``.bin`` / ``.safetensors`` state dict is accepted as well."""
         if state_dict is None:
             state_dict = self.vision_tower_name
+        self.image_processor = _default_image_processor(state_dict if isinstance(state_dict, str) else None)
         if isinstance(state_dict, str):
             state_dict = _load_clip_state_dict(state_dict)
         dev = self.weight_blob.device
@@ -104,6 +124,12 @@ class CLIPVisionTower(nn.Module):
         b = self.weight_blob[int(y.b_fc2): int(y.b_fc2) + 1024 * 4].view(torch.float32)
         return w, b
 
+    def preprocess_u8(self, frames: torch.Tensor) -> torch.Tensor:
+        """Decoded frames uint8 [N,H,W,3] on the device -> uint8 [N,224,224,3]: this tower's ``image_processor`` resize +
+        centre crop as one kernel, bit-identical to PIL (hoi_forecast/dataset/video_utils.py:28-53 does it per frame on the
+        CPU).  The result goes straight into ``forward`` / ``forward_hidden`` (rescale + normalise are fused there)."""
+        return ops.resize_center_crop_u8(frames.to(self.device), _CFG["image_size"])
+
     @torch.no_grad()
     def forward(self, images):
         if type(images) is list:
@@ -123,7 +149,7 @@ class CLIPVisionTower(nn.Module):
 
     @property
     def dtype(self):
-        return self._dtype
+        return self._dtype_probe.dtype
 
     @property
     def device(self):

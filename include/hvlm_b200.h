@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HVLM_ABI_VERSION 1
+#define HVLM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HVLM_API __attribute__((visibility("default")))
@@ -204,6 +204,12 @@ HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok
  *                             (process_traj_positional_embedding, handsonvlm.py:310-338).
  * L is chosen by the caller: T-1+Nv when every sample has exactly one image token (the collator's
  * contract, hybrid_dataset.py:155-158), else max(lens) after reading `lens` back.
+ * last_visual_end (optional device int64 scalar): the reference's `self.last_visual_token_index` side effect
+ *                             (handsonvlm.py:288) = position of the last image token of the last sample that has one,
+ *                             relative to the ids left after the previous image token, + its number of visual rows.
+ *                             Left untouched when no sample has an image token.
+ * Limit: at most 64 image tokens per sample (HVLM_PLAN_ERR_IMG_OVERFLOW beyond; the reference has no limit, its
+ *        collators emit one).
  * ---------------------------------------------------------------------------------------------- */
 /* OR-able into `variant` of hvlm_splice_plan / hvlm_splice_fwd: the `tune_mm_mlp_adapter && mm_use_im_start_end` branch of
  * llava_arch.py:146-161,172-173 -- the embeddings are the same rows, but the token right after an image token (<im_end>)
@@ -226,7 +232,8 @@ HVLM_API int hvlm_splice_plan(const int64_t* ids, const int32_t* counts /*from h
                      int n_img, int L, int vocab, int variant,
                      int hand_mode /*0 none, 1 training (4 points, cnt/4 scaling), 2 eval (n points)*/,
                      int n_hand_points, int32_t* src_index, int8_t* hand_code, int32_t* lens,
-                     float* hand_scale /*[B]*/, int32_t* status, void* stream);
+                     float* hand_scale /*[B]*/, int32_t* status,
+                     int64_t* last_visual_end /*NULL ok: device scalar, see below*/, void* stream);
 /* Same plan for visual token blocks of DIFFERENT lengths per image slot -- the list path of images_to_tokens
  * (llava_arch.py:95-106: each sample's image group becomes one flat [n_i*256, D] block and its single image token expands to
  * all of it).  slot_offsets int32 [n_slots+1] (device): rows of slot g are visual[slot_offsets[g] .. slot_offsets[g+1]) of
@@ -234,7 +241,7 @@ HVLM_API int hvlm_splice_plan(const int64_t* ids, const int32_t* counts /*from h
 HVLM_API int hvlm_splice_plan_ragged(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B, int T,
                             int n_slots, int L, int vocab, int variant, int hand_mode, int n_hand_points,
                             int32_t* src_index, int8_t* hand_code, int32_t* lens, float* hand_scale, int32_t* status,
-                            void* stream);
+                            int64_t* last_visual_end /*NULL ok*/, void* stream);
 HVLM_API int hvlm_splice_fwd(const int32_t* src_index, const int8_t* hand_code, const int32_t* lens, const float* hand_scale,
                     const int64_t* ids, const int64_t* labels /*NULL ok*/, const uint8_t* mask /*NULL ok*/,
                     const void* embed_table, const void* visual, const uint8_t* visual_mask /*NULL = all true*/,
@@ -286,6 +293,51 @@ HVLM_API int hvlm_traj_decode(const void* cond, int64_t ld_cond, int interleaved
  * act: 0 none, 1 ReLU, 2 ELU. */
 HVLM_API int hvlm_skinny_linear(const void* x, int64_t ld_x, const void* W, const void* b, int act, int dtype, int R, int K,
                        int H, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame de-duplication in front of the tower.  Real clips repeat frames: EPIC clips are 10 distinct
+ * frames tiled x10 (handsonvlm/dataset/epic_dataset.py:90-95, handsonvlm/evaluation/handsonvlm_inference.py:205), single
+ * images are tiled x100 (handsonvlm/dataset/hybrid_dataset.py:141-142); the reference encodes every copy.
+ * frames   [n_frames] rows of frame_bytes bytes (any dtype / layout; frame_bytes % 16 == 0, base 16-byte aligned)
+ * frame_map int32 [n_frames]: index of frame i's representative in the compacted list (-> hvlm_pool_slowfast_fwd_mapped)
+ * rep       int32 [n_frames]: rep[u] = first frame with unique index u, u < *n_unique; entries past *n_unique are 0, so a
+ *           gather of a fixed capacity (hvlm_gather_rows with n_out = capacity) is always in bounds
+ * n_unique  int32 device scalar
+ * capacity  0, or the number of distinct frames the caller has sized its buffers for WITHOUT reading n_unique back (a
+ *           per-dataset contract, e.g. 10 per EPIC clip): frame_map is then clamped to capacity-1 so that every later
+ *           access stays in bounds, and *n_unique > capacity tells the caller (asynchronously) that the contract broke
+ * Two frames are duplicates iff their bytes are equal: a 64-bit checksum groups candidates (one streaming pass), a
+ * byte-wise comparison against the first frame of the group confirms them (second pass over the duplicates only); a
+ * checksum collision just leaves the frame un-deduplicated.  Deterministic.  No host synchronisation.
+ * workspace: hvlm_frame_dedup_workspace_bytes(n_frames) bytes, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API size_t hvlm_frame_dedup_workspace_bytes(int n_frames);
+HVLM_API int hvlm_frame_dedup(const void* frames, size_t frame_bytes, int n_frames, int capacity, int32_t* frame_map,
+                              int32_t* rep, int32_t* n_unique, void* workspace, size_t workspace_bytes, void* stream);
+/* dst[i, :] = src[idx[i], :] for i < n_out; rows of row_bytes bytes (% 16 == 0); idx int32 (device), values in [0, n_src). */
+HVLM_API int hvlm_gather_rows(const void* src, size_t row_bytes, int n_src, const int32_t* idx, int n_out, void* dst,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CLIPImageProcessor resize + centre crop on raw decoded frames -- replaces the CPU side of
+ *   hoi_forecast/dataset/video_utils.py:28-53 (processor.preprocess per frame; transformers==4.31.0
+ *   CLIPImageProcessor: resize shortest edge -> 224 with PIL BICUBIC, centre crop 224x224; the rescale + normalise that
+ *   follow are fused into hvlm_vit_l14_fwd_u8).
+ * The arithmetic is Pillow's 8-bit ImagingResample restated: separable filter, horizontal pass then vertical pass, 22-bit
+ * fixed-point coefficients, rounding + clipping to uint8 after EACH pass -- results are bit-identical to
+ * PIL.Image.resize(..., BICUBIC) followed by the crop.
+ * hvlm_resize_table_host (HOST function, no CUDA): coefficient table of one axis for the output window
+ *   [crop0, crop0 + crop_n) of an in_size -> out_size bicubic resize.  bounds_host int32 [2*crop_n] = (first input index,
+ *   number of taps) per output index; coef_host int32 [crop_n * ksize] fixed-point taps (zero padded); returns ksize
+ *   (> 0), or a negative hvlm_status.  Call with coef_host == NULL to query ksize only.
+ * hvlm_resize_crop_u8: src uint8 [N, H, W, 3] -> dst uint8 [N, out_h, out_w, 3]; x / y tables (DEVICE copies of the host
+ *   tables above) for out_w / out_h output indices.
+ * ---------------------------------------------------------------------------------------------- */
+HVLM_API int hvlm_resize_table_host(int in_size, int out_size, int crop0, int crop_n, int32_t* bounds_host,
+                                    int32_t* coef_host);
+HVLM_API int hvlm_resize_crop_u8(const uint8_t* src, int N, int H, int W, uint8_t* dst, int out_h, int out_w,
+                                 const int32_t* xbounds, const int32_t* xcoef, int xk, const int32_t* ybounds,
+                                 const int32_t* ycoef, int yk, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * helpers for the training-shaped variant

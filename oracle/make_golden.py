@@ -18,6 +18,7 @@ Sources exercised (reference checkout, unmodified):
 from __future__ import annotations
 
 import os
+import sys
 import textwrap
 import types
 
@@ -193,6 +194,13 @@ def golden_splice(ns):
     ids = torch.cat([synth._rand_ids("h", 9, 27), torch.tensor([synth.IMAGE_TOKEN_INDEX])]).unsqueeze(0)
     run_hvlm("splice_hvlm_empty_tail", ids, torch.ones_like(ids, dtype=torch.bool), ids.clone(),
              synth.gen("fh", (1, 2, 4, 2), 1.0, 27), torch.ones(1, 2, dtype=torch.bool))
+
+    # (i) two image tokens in sample 0 (it consumes visual slots 0 and 1), none in sample 1: the surviving
+    #     last_visual_token_index is the SECOND token's position relative to the ids left after the first one
+    ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=2, seed=28, n_pre=6, n_post=5)
+    ids[0, 10] = synth.IMAGE_TOKEN_INDEX
+    ids[1, 6] = 4321
+    run_hvlm("splice_hvlm_two_images", ids, mask, labels, fh, fv)
 
     # LLaVA / LITA variant (image input: [B,3,224,224] -> 256 tokens), config-1 shaped
     LV = ns.llava_arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal
@@ -383,6 +391,11 @@ def main():
     ns = ref_shim.load()
     if ns.handsonvlm is None:
         raise ns.handsonvlm_error
+    only = sys.argv[1:]
+    if only:                                  # e.g. `python -m oracle.make_golden golden_splice`
+        for name in only:
+            globals()[name](ns)
+        return
     golden_pool(ns)
     golden_gather(ns)
     golden_traj(ns)

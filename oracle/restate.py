@@ -321,6 +321,21 @@ def splice(ids, attention_mask, labels, visual, embed_w, variant: str,
     return new_mask, embeds, new_labels
 
 
+def last_visual_token_index(ids: torch.Tensor, Nv: int, previous: int = -1) -> int:
+    """handsonvlm.py:288 side effect: ``self.last_visual_token_index = image_token_start + n_visual_tokens`` is assigned for
+    every image token of every sample in order; ``image_token_start`` indexes ``cur_input_ids`` AFTER the slices of
+    handsonvlm.py:300-303 (everything up to and including the previous image token cut off).  Samples without an image
+    token leave it alone (:234-245)."""
+    val = previous
+    for row in ids:
+        pos = (row == IMAGE_TOKEN_INDEX).nonzero().flatten().tolist()
+        prev = -1
+        for p in pos:
+            val = (p - prev - 1) + Nv
+            prev = p
+    return val
+
+
 def splice_backward(d_embeds, ids, Nv: int, n_img: int, vocab: int, im_start_end: bool = False):
     """Backward of the copy part of the splice: visual rows -> d_visual [n_img,Nv,D];
     text rows scatter-add into d_embed_table [vocab, D].  With ``im_start_end`` only the tokens
@@ -451,3 +466,112 @@ def projector_grads(feats_pooled: torch.Tensor, d_tokens: torch.Tensor):
     x = feats_pooled.reshape(-1, feats_pooled.shape[-1]).float()
     dy = d_tokens.reshape(-1, d_tokens.shape[-1]).float()
     return dy.t() @ x, dy.sum(0)
+
+
+# ----------------------------------------------------------------------------------------
+# f3: CLIPImageProcessor resize + centre crop (hoi_forecast/dataset/video_utils.py:28-53 ->
+#     processor.preprocess; transformers==4.31.0 models/clip/image_processing_clip.py: resize
+#     shortest edge -> 224 with PIL BICUBIC, centre crop 224, rescale 1/255, normalise).
+# Third party: Pillow's 8-bit resampler (src/libImaging/Resample.c), restated from its published
+# algorithm in integer numpy; pinned against PIL.Image.resize itself by tests/test_oracle_golden.py.
+# ----------------------------------------------------------------------------------------
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def _bicubic(x: float) -> float:
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def resample_table(in_size: int, out_size: int):
+    """Pillow precompute_coeffs + normalize_coeffs_8bpc for a bicubic in_size -> out_size pass:
+    (bounds int [out,2] = (xmin, n_taps), coef int [out, ksize])."""
+    scale = float(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    coef = np.zeros((out_size, ksize), np.int64)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        for x, v in enumerate(w):
+            coef[xx, x] = int(-0.5 + v * (1 << _PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << _PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, coef
+
+
+def _resample_axis_last(img: np.ndarray, bounds: np.ndarray, coef: np.ndarray) -> np.ndarray:
+    """img uint8 [..., in] -> uint8 [..., out] along the last axis (one 8-bit Pillow pass)."""
+    out = np.empty(img.shape[:-1] + (bounds.shape[0],), np.uint8)
+    src = img.astype(np.int64)
+    for xx in range(bounds.shape[0]):
+        x0, n = int(bounds[xx, 0]), int(bounds[xx, 1])
+        acc = (1 << (_PRECISION_BITS - 1)) + (src[..., x0:x0 + n] * coef[xx, :n]).sum(-1)
+        out[..., xx] = np.clip(acc >> _PRECISION_BITS, 0, 255).astype(np.uint8)
+    return out
+
+
+def clip_resize_output_size(h: int, w: int, shortest: int = 224):
+    """transformers get_resize_output_image_size(size=int, default_to_square=False) -> (new_h, new_w)."""
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = shortest, int(shortest * long / short)
+    return (new_long, new_short) if w <= h else (new_short, new_long)
+
+
+def clip_resize_center_crop_u8(frames: np.ndarray, size: int = 224) -> np.ndarray:
+    """frames uint8 [N,H,W,3] -> uint8 [N,size,size,3]: PIL BICUBIC resize of the shortest edge to `size` (horizontal
+    pass first, then vertical, uint8 in between), then transformers' centre crop."""
+    N, H, W, _ = frames.shape
+    nh, nw = clip_resize_output_size(H, W, size)
+    xb, xc = resample_table(W, nw)
+    yb, yc = resample_table(H, nh)
+    tmp = _resample_axis_last(np.ascontiguousarray(frames.transpose(0, 1, 3, 2)), xb, xc)      # [N,H,3,nw]
+    out = _resample_axis_last(np.ascontiguousarray(tmp.transpose(0, 2, 3, 1)), yb, yc)         # [N,3,nw,nh]
+    out = out.transpose(0, 3, 2, 1)                                                            # [N,nh,nw,3]
+    top, left = (nh - size) // 2, (nw - size) // 2
+    return np.ascontiguousarray(out[:, top:top + size, left:left + size])
+
+
+def clip_normalize_u8(frames: np.ndarray) -> torch.Tensor:
+    """uint8 [N,h,w,3] -> float32 [N,3,h,w]: rescale 1/255 + CLIP mean/std normalisation."""
+    x = torch.from_numpy(frames).float().mul(1.0 / 255.0)
+    x = (x - torch.tensor(CLIP_MEAN)) / torch.tensor(CLIP_STD)
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# f2: frame de-duplication -- the reference has none (it encodes every repeated frame:
+#     epic_dataset.py:90-95, hybrid_dataset.py:141-142); the specification is "same visual
+#     tokens as without it", plus this definition of the frame map.
+# ----------------------------------------------------------------------------------------
+
+def frame_dedup(frames: torch.Tensor):
+    """frames [N, ...] -> (frame_map int32 [N], rep int32 [U]): byte-wise equal frames share the
+    unique index of their first occurrence; unique indices are numbered in order of first occurrence."""
+    N = frames.shape[0]
+    raw = frames.contiguous().reshape(N, -1).view(torch.uint8).numpy()
+    first, fmap, rep = {}, [], []
+    for i in range(N):
+        key = raw[i].tobytes()
+        if key not in first:
+            first[key] = len(rep)
+            rep.append(i)
+        fmap.append(first[key])
+    return torch.tensor(fmap, dtype=torch.int32), torch.tensor(rep, dtype=torch.int32)

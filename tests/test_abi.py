@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.hvlm_abi_version() == 1
+    assert lib.hvlm_abi_version() == hvlm_b200._lib.ABI_VERSION
     assert L.strerror(0) == "ok"
     assert "aligned" in L.strerror(-4)
     assert "unknown" in L.strerror(-99)

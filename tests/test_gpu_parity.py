@@ -369,7 +369,7 @@ def _splice_cuda(variant, ids, mask, labels, vis, table, fh=None, is_eval=False,
 @pytest.mark.parametrize("name,is_eval", [
     ("splice_hvlm_train_b3", False), ("splice_hvlm_train_padded", False), ("splice_hvlm_2hand", False),
     ("splice_hvlm_0hand", False), ("splice_hvlm_ragged", False), ("splice_hvlm_eval_hands", True),
-    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False)])
+    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False), ("splice_hvlm_two_images", False)])
 def test_splice_handsonvlm_vs_reference_fixture(golden, small, name, is_eval):
     g = golden(name)
     ids = T(g["ids"])
@@ -981,29 +981,4 @@ def test_uint8_frames_with_fused_clip_normalisation(tower23):
         tw.forward_hidden(torch.zeros(1, 3, 224, 224, dtype=torch.uint8, device=DEV))
 
 
-def test_frame_dedup_tiled_clip(tower23):
-    """an EPIC-style clip (10 distinct frames tiled x10) is encoded once per distinct frame; tokens are
-    bit-identical to the undeduplicated path, and the tower launches ~10x fewer frames."""
-    tw, sd = tower23("hf")
-    D = 256
-    ps = synth.projector_state(D)
-    proj = torch.nn.Linear(1024, D)
-    proj.weight.data.copy_(ps["mm_projector.weight"])
-    proj.bias.data.copy_(ps["mm_projector.bias"])
-    proj = proj.to(DEV)
-    base = synth.pixels((4, 3, 224, 224), seed=21).to(torch.bfloat16)
-    clip = base.repeat_interleave(5, dim=0).unsqueeze(0).to(DEV)          # [1,20,3,224,224], 4 distinct frames
-    d = arch.distinct_frames(clip[0])
-    assert d is not None and d[0].numel() == 4
-    assert d[0][d[1].long()].tolist() == [5 * (i // 5) for i in range(20)]      # every frame -> first occurrence
-    assert arch.distinct_frames(synth.pixels((5, 3, 224, 224), seed=22).to(DEV)) is None
-    with torch.no_grad():
-        for mode in ("temporal_spatial_pool", "spatial_pool", "temporal", "spatial", "none"):
-            ref = arch.video_tokens(tw, proj, clip, mode, dedup=False)
-            out = arch.video_tokens(tw, proj, clip, mode, dedup=True)
-            assert torch.equal(out, ref), mode
-    # mixed batch: two clips sharing frames across the batch dimension
-    clip2 = torch.cat([clip, clip.flip(1)], 0)
-    with torch.no_grad():
-        assert torch.equal(arch.video_tokens(tw, proj, clip2, "temporal_spatial_pool", True),
-                           arch.video_tokens(tw, proj, clip2, "temporal_spatial_pool", False))
+# frame de-duplication: tests/test_gpu_round2.py (kernel vs oracle frame map, tokens vs oracle numbers, static capacity)

@@ -165,7 +165,7 @@ def _check_splice(g, mask2, e2, l2, tol=2e-5):
 @pytest.mark.parametrize("name,is_eval", [
     ("splice_hvlm_train_b3", False), ("splice_hvlm_train_padded", False), ("splice_hvlm_2hand", False),
     ("splice_hvlm_0hand", False), ("splice_hvlm_ragged", False), ("splice_hvlm_eval_hands", True),
-    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False)])
+    ("splice_hvlm_eval_nohands", True), ("splice_hvlm_empty_tail", False), ("splice_hvlm_two_images", False)])
 def test_splice_handsonvlm(golden, small, name, is_eval):
     g = golden(name)
     ids = T(g["ids"])
@@ -178,11 +178,13 @@ def test_splice_handsonvlm(golden, small, name, is_eval):
     m2, e2, l2 = restate.splice(ids, mask, labels, vis, small[3], "handsonvlm", future_hands=fh,
                                 is_evaluate=is_eval)
     _check_splice(g, m2, e2, l2)
+    # the reference's write-only side effect (handsonvlm.py:288), as the reference left it after this call
+    assert restate.last_visual_token_index(ids, vis.shape[1]) == int(g["last_visual_token_index"])
     # text rows are exact copies of embedding rows, visual rows exact copies of pipeline() output
     plan, _ = restate.splice_plan(ids[0], vis.shape[1])
     for r, (kind, idx) in enumerate(plan):
         if kind == 1:
-            assert torch.equal(e2[0, r], vis[0, idx])
+            assert torch.equal(e2[0, r], vis.reshape(-1, vis.shape[-1])[idx])   # sample 0 owns visual slots 0..k-1
 
 
 @pytest.mark.parametrize("name,pxshape,pxseed,cfg", [
@@ -286,3 +288,67 @@ def test_pool_first_equals_project_first():
     a = restate.pool_tokens(restate.project(x, w, b), "temporal_spatial_pool")
     c = restate.project(restate.pool_tokens(x, "temporal_spatial_pool"), w, b)
     assert relmax(c, a) <= 1e-5
+
+
+# ------------------------------------------------------------------ f3: CLIPImageProcessor resize + centre crop
+@pytest.mark.parametrize("H,W", [(256, 456), (224, 224), (480, 640), (300, 200), (225, 230), (720, 1280)])
+def test_resize_center_crop_restatement_is_pil_exact(H, W):
+    """The integer restatement of Pillow's 8-bit bicubic resampler + transformers' centre crop against PIL itself
+    (what transformers==4.31.0's CLIPImageProcessor runs, hoi_forecast/dataset/video_utils.py:47-52): bit-exact."""
+    from PIL import Image
+    rng = np.random.RandomState(H * 1000 + W)
+    frames = rng.randint(0, 256, (2, H, W, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    frames[1] = np.stack([(xx * 255 // max(W - 1, 1)), (yy * 255 // max(H - 1, 1)), ((xx + yy) % 256)], -1).astype(np.uint8)
+    out = restate.clip_resize_center_crop_u8(frames)
+    nh, nw = restate.clip_resize_output_size(H, W)
+    top, left = (nh - 224) // 2, (nw - 224) // 2
+    for i in range(2):
+        ref = np.asarray(Image.fromarray(frames[i]).resize((nw, nh), resample=Image.BICUBIC))[top:top + 224, left:left + 224]
+        assert np.array_equal(out[i], ref)
+
+
+def test_resize_restatement_matches_hf_pil_processor():
+    """End of the preprocessing chain against HuggingFace's PIL-backed CLIPImageProcessor (the 4.31-era code path):
+    resize + crop + rescale + normalise -> float pixels."""
+    import transformers
+    from PIL import Image
+    cls = getattr(transformers.models.clip, "CLIPImageProcessorPil", None)
+    if cls is None:
+        pytest.skip("this transformers has no PIL-backed CLIPImageProcessor")
+    frames = np.random.RandomState(5).randint(0, 256, (1, 256, 456, 3), dtype=np.uint8)     # EPIC-KITCHENS frame size
+    ref = cls().preprocess(Image.fromarray(frames[0]), return_tensors="pt")["pixel_values"][0]
+    mine = restate.clip_normalize_u8(restate.clip_resize_center_crop_u8(frames))[0]
+    assert float((ref - mine).abs().max()) <= 1e-6
+
+
+def test_resize_host_tables_match_restatement():
+    """hvlm_resize_table_host (pure host code of the C ABI, no GPU needed) == the oracle's coefficient tables."""
+    import ctypes as C
+    import hvlm_b200
+    lib = hvlm_b200._lib.lib()
+    for i, o in [(456, 399), (256, 224), (224, 224), (1280, 398), (200, 224)]:
+        k = lib.hvlm_resize_table_host(i, o, 0, o, None, None)
+        b = (C.c_int32 * (2 * o))()
+        c = (C.c_int32 * (o * k))()
+        assert lib.hvlm_resize_table_host(i, o, 0, o, b, c) == k
+        rb, rc = restate.resample_table(i, o)
+        assert np.array_equal(np.array(b).reshape(o, 2), rb) and np.array_equal(np.array(c).reshape(o, k), rc)
+    # a crop window is the same table, sliced
+    k = lib.hvlm_resize_table_host(456, 399, 87, 224, None, None)
+    b = (C.c_int32 * (2 * 224))()
+    c = (C.c_int32 * (224 * k))()
+    assert lib.hvlm_resize_table_host(456, 399, 87, 224, b, c) == k
+    rb, rc = restate.resample_table(456, 399)
+    assert np.array_equal(np.array(b).reshape(224, 2), rb[87:311]) and np.array_equal(np.array(c).reshape(224, k), rc[87:311])
+    assert lib.hvlm_resize_table_host(456, 399, 300, 224, b, c) < 0
+
+
+def test_frame_dedup_restatement():
+    x = synth.pixels((3, 3, 8, 8), seed=1)
+    clip = x[[0, 1, 0, 2, 1, 1]]
+    fmap, rep = restate.frame_dedup(clip)
+    assert fmap.tolist() == [0, 1, 0, 2, 1, 1] and rep.tolist() == [0, 1, 3]
+    neg0 = torch.zeros(2, 4)
+    neg0[1] = -0.0                       # byte-wise comparison: +0 and -0 are different frames
+    assert restate.frame_dedup(neg0)[1].tolist() == [0, 1]
