@@ -93,3 +93,39 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|oracle[./]", txt, re.M), f"{f} references oracle/"
+
+
+def test_new_entries_validate_arguments_without_gpu(lib):
+    null = C.c_void_p(0)
+    assert lib.hvlm_frame_dedup(null, 16, 1, 0, null, null, null, null, 0, null) == -1
+    assert lib.hvlm_frame_dedup_workspace_bytes(100) >= 100 * 16 and lib.hvlm_frame_dedup_workspace_bytes(0) == 0
+    assert lib.hvlm_gather_rows(null, 16, 1, null, 1, null, null) == -1
+    assert lib.hvlm_resize_crop_u8(null, 1, 1, 1, null, 1, 1, null, null, 1, null, null, 1, null) == -1
+    assert lib.hvlm_resize_table_host(0, 224, 0, 224, None, None) == -1
+    assert lib.hvlm_resize_table_host(456, 399, 87, 224, None, None) == 7       # ksize query
+
+
+def test_sass_proves_tcgen05_tmem_tma():
+    """The contraction kernels are Blackwell-native in the BUILT library: tcgen05.mma (UTCHMMA, cta_group::2 for the 2-CTA
+    GEMM), TMEM loads (LDTM; STTM for the attention's P write-back), TMA loads / stores / reduce-adds (UTMALDG / UTMASTG /
+    UTMAREDG) -- and no legacy mma.sync (HMMA) anywhere.  profiles/sass_summary.txt is this table, committed."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_summary
+    ks = sass_summary.summarize(L.LIB_PATH)
+    g2 = {k: v for k, v in ks.items() if "gemm2_tcgen05_kernel" in k}
+    g1 = {k: v for k, v in ks.items() if k.startswith("gemm_tcgen05_kernel")}
+    at = {k: v for k, v in ks.items() if "attn_tcgen05_kernel" in k}
+    assert len(g2) >= 8 and len(g1) >= 8 and len(at) == 1
+    for v in g2.values():
+        assert v["UTCHMMA.2CTA"] > 0 and v["UTCHMMA"] == 0 and v["LDTM"] > 0 and v["UTMALDG"] > 0
+        assert v["UTMASTG"] + v["UTMAREDG"] > 0 and v["UTCBAR"] > 0
+    for v in g1.values():
+        assert v["UTCHMMA"] > 0 and v["LDTM"] > 0 and v["UTMALDG"] > 0
+    a = next(iter(at.values()))
+    assert a["UTCHMMA"] > 0 and a["LDTM"] > 0 and a["STTM"] > 0 and a["UTMALDG"] > 0 and a["MUFU"] > 0
+    assert any(v["UTMAREDG"] > 0 for v in g2.values())            # the residual GEMM's reduce-add into the fp32 stream
+    assert all(v["HMMA"] == 0 for v in ks.values())

@@ -381,10 +381,12 @@ def test_frame_dedup_tokens_vs_oracle(tower_hf):
         arch.check_deferred_status(host)                                   # contract held: nothing raises
         assert torch.equal(r[3][0, 35:35 + 20 + 256].float(), plain_tsp(tw, proj, clip)[0].float())
         # contract broken: 4 distinct frames, capacity 2 per clip -> reported by the deferred check, not silently wrong
+        # (by the first poll that finds the copied-out count: the same call's splice, or check_deferred_status)
         host.config.hvlm_dedup_frames = 2
-        host.prepare_inputs_labels_for_multimodal(*args, **kw)
         with pytest.raises(RuntimeError, match="distinct frames"):
+            host.prepare_inputs_labels_for_multimodal(*args, **kw)
             arch.check_deferred_status(host)
+        host.__dict__.pop("_hvlm_deferred", None)
         assert n_dedup < 7 * 23 + 40
 
 
