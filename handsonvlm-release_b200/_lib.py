@@ -41,6 +41,11 @@ class VitLayout(C.Structure):
                 ("n_layers", C.c_int32), ("_pad", C.c_int32)]
 
 
+class ResizePlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("in_h", "in_w", "new_h", "new_w", "top", "left", "out_h", "out_w", "xk", "yk", "x_lo",
+                                         "x_cols", "rows_cap", "table_ints")]
+
+
 # symbol -> (restype, argtypes); must list every HVLM_API symbol of the header (tests/test_abi.py checks it)
 SIGNATURES = {
     "hvlm_strerror": (C.c_char_p, [i32]),
@@ -75,7 +80,9 @@ SIGNATURES = {
     "hvlm_frame_dedup": (i32, [p, sz, i32, i32, p, p, p, p, sz, p]),
     "hvlm_gather_rows": (i32, [p, sz, i32, p, i32, p, p]),
     "hvlm_resize_table_host": (i32, [i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    "hvlm_resize_crop_u8": (i32, [p, i32, i32, i32, p, i32, i32, p, p, i32, p, p, i32, p]),
+    "hvlm_resize_plan_host": (i32, [i32, i32, i32, i32, p]),
+    "hvlm_resize_tables_host": (i32, [p, C.POINTER(C.c_int32)]),
+    "hvlm_resize_crop_u8": (i32, [p, i32, p, p, p, p]),
     "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
     "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
     "hvlm_launch_count": (C.c_uint64, []),

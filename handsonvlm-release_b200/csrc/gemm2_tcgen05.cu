@@ -602,7 +602,7 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
     }();
     static const int resid_load_maxk = []() {
         const char* e = getenv("HVLM_RESID_LOAD_MAXK");
-        return e ? atoi(e) : 1024;
+        return e ? atoi(e) : 0;
     }();
     if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
         return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
@@ -618,9 +618,11 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
                 return launch_two<EPI_RESID_F32, true>(A, B, M, N, K, ep, s);
             }
             // Short-K residual GEMMs (out_proj, K = 1024) are bound by their epilogue: the fp32 TMA reduce-add into the
-            // residual stream sustains ~7 B/clk/SM, twice the time of the K loop.  For K <= HVLM_RESID_LOAD_MAXK (default
-            // 1024; 0 disables) the epilogue TMA-loads the residual tile two units ahead, adds in shared memory and leaves
-            // with a plain TMA store.  Long-K GEMMs (fc2) hide the reduce-add behind the K loop and keep it.
+            // residual stream sustains ~7 B/clk/SM, twice the time of the K loop.  Experiment (HVLM_RESID_LOAD_MAXK=1024;
+            // default 0 = off): the epilogue TMA-loads the residual tile two units ahead, adds in shared memory and leaves
+            // with a plain TMA store.  Correct (same tests), but measured SLOWER on B200, same box, 100 frames: out_proj
+            // 74.3 vs 66.7 us per call, step 14.91 vs 14.52 ms -- the extra 32 KB of shared-memory traffic per unit (TMA
+            // write + read-modify-write) competes with the tensor cores' operand reads; the L2-side reduce-add stays.
             if (K <= resid_load_maxk) return launch_two<EPI_RESID_F32, false, 1, true>(A, B, M, N, K, ep, s);
             return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
         case EPI_QKV_HM: return launch_two<EPI_QKV_HM>(A, B, M, N, K, ep, s);

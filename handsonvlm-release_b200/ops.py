@@ -738,33 +738,23 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, n_out: Optional[int] = Non
     return out
 
 
-_resize_tables: dict = {}
+_resize_plans: dict = {}
 
 
-def resize_tables(in_size: int, out_size: int, crop0: int, crop_n: int, device) -> Tuple[torch.Tensor, torch.Tensor, int]:
-    """Pillow bicubic coefficient table of one axis (hvlm_resize_table_host), cached on the device per geometry."""
-    key = (in_size, out_size, crop0, crop_n, str(device))
-    hit = _resize_tables.get(key)
+def resize_plan(H: int, W: int, size: int, device):
+    """(hvlm_resize_plan, device coefficient table) for decoded frames of H x W, cached per geometry and device: geometry
+    as transformers derives it (shortest edge -> size, centre crop size x size), Pillow's fixed-point bicubic taps."""
+    key = (H, W, size, str(device))
+    hit = _resize_plans.get(key)
     if hit is None:
         lib = L.lib()
-        k = lib.hvlm_resize_table_host(in_size, out_size, crop0, crop_n, None, None)
-        if k <= 0:
-            raise L.HvlmError("hvlm_resize_table_host", k)
-        bounds = (C.c_int32 * (2 * crop_n))()
-        coef = (C.c_int32 * (crop_n * k))()
-        rc = lib.hvlm_resize_table_host(in_size, out_size, crop0, crop_n, bounds, coef)
-        if rc != k:
-            raise L.HvlmError("hvlm_resize_table_host", rc)
-        hit = (torch.tensor(list(bounds), dtype=torch.int32).to(device), torch.tensor(list(coef), dtype=torch.int32).to(device), k)
-        _resize_tables[key] = hit
+        plan = L.ResizePlan()
+        L.check(lib.hvlm_resize_plan_host(H, W, size, size, C.byref(plan)), "hvlm_resize_plan_host")
+        tab = (C.c_int32 * plan.table_ints)()
+        L.check(lib.hvlm_resize_tables_host(C.byref(plan), tab), "hvlm_resize_tables_host")
+        hit = (plan, torch.frombuffer(tab, dtype=torch.int32).clone().to(device))
+        _resize_plans[key] = hit
     return hit
-
-
-def clip_resize_output_size(h: int, w: int, shortest: int = 224) -> Tuple[int, int]:
-    """transformers get_resize_output_image_size(size=int, default_to_square=False): (new_h, new_w)."""
-    short, long = (w, h) if w <= h else (h, w)
-    new_short, new_long = shortest, int(shortest * long / short)
-    return (new_long, new_short) if w <= h else (new_short, new_long)
 
 
 def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor:
@@ -776,11 +766,7 @@ def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor
         raise ValueError(f"expected uint8 frames [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
     frames = frames.contiguous()
     N, H, W, _ = frames.shape
-    nh, nw = clip_resize_output_size(H, W, size)
-    top, left = (nh - size) // 2, (nw - size) // 2
-    xb, xc, xk = resize_tables(W, nw, left, size, frames.device)
-    yb, yc, yk = resize_tables(H, nh, top, size, frames.device)
+    plan, table = resize_plan(H, W, size, frames.device)
     out = torch.empty(N, size, size, 3, dtype=torch.uint8, device=frames.device)
-    L.check(L.lib().hvlm_resize_crop_u8(_p(frames), N, H, W, _p(out), size, size, _p(xb), _p(xc), xk, _p(yb), _p(yc), yk,
-                                        _stream()), "hvlm_resize_crop_u8")
+    L.check(L.lib().hvlm_resize_crop_u8(_p(frames), N, C.byref(plan), _p(table), _p(out), _stream()), "hvlm_resize_crop_u8")
     return out

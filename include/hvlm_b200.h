@@ -326,18 +326,31 @@ HVLM_API int hvlm_gather_rows(const void* src, size_t row_bytes, int n_src, cons
  * The arithmetic is Pillow's 8-bit ImagingResample restated: separable filter, horizontal pass then vertical pass, 22-bit
  * fixed-point coefficients, rounding + clipping to uint8 after EACH pass -- results are bit-identical to
  * PIL.Image.resize(..., BICUBIC) followed by the crop.
- * hvlm_resize_table_host (HOST function, no CUDA): coefficient table of one axis for the output window
- *   [crop0, crop0 + crop_n) of an in_size -> out_size bicubic resize.  bounds_host int32 [2*crop_n] = (first input index,
- *   number of taps) per output index; coef_host int32 [crop_n * ksize] fixed-point taps (zero padded); returns ksize
- *   (> 0), or a negative hvlm_status.  Call with coef_host == NULL to query ksize only.
- * hvlm_resize_crop_u8: src uint8 [N, H, W, 3] -> dst uint8 [N, out_h, out_w, 3]; x / y tables (DEVICE copies of the host
- *   tables above) for out_w / out_h output indices.
+ * Host side (pure host code, no CUDA): hvlm_resize_plan_host derives the geometry the way transformers does
+ *   (get_resize_output_image_size with an int size / center_crop), hvlm_resize_tables_host fills the fixed-point
+ *   coefficient table (plan->table_ints int32: xb [2*out_w] | xc [out_w*xk] | yb [2*out_h] | yc [out_h*yk], b = (first
+ *   source index, taps) per output index of the crop window); the caller copies the table to the device once per geometry.
+ *   hvlm_resize_table_host is the single-axis building block (Pillow precompute_coeffs + normalize_coeffs_8bpc for the
+ *   output window [crop0, crop0 + crop_n) of an in_size -> out_size pass; returns ksize, or with coef_host == NULL only
+ *   queries it).
+ * hvlm_resize_crop_u8: src uint8 [N, in_h, in_w, 3] -> dst uint8 [N, out_h, out_w, 3] (dst 4-byte aligned).
  * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t in_h, in_w;     /* decoded frame size                                                  */
+    int32_t new_h, new_w;   /* size after the shortest-edge resize                                 */
+    int32_t top, left;      /* centre-crop offsets inside the resized image                        */
+    int32_t out_h, out_w;   /* crop size (224 x 224 for CLIP ViT-L/14)                             */
+    int32_t xk, yk;         /* filter taps per output column / row                                 */
+    int32_t x_lo, x_cols;   /* source columns [x_lo, x_lo + x_cols) the crop window reads          */
+    int32_t rows_cap;       /* most source rows any block of 8 output rows reads                   */
+    int32_t table_ints;     /* int32 entries of the coefficient table                              */
+} hvlm_resize_plan;
+HVLM_API int hvlm_resize_plan_host(int in_h, int in_w, int shortest_edge, int crop, hvlm_resize_plan* plan_host);
+HVLM_API int hvlm_resize_tables_host(const hvlm_resize_plan* plan_host, int32_t* table_host);
 HVLM_API int hvlm_resize_table_host(int in_size, int out_size, int crop0, int crop_n, int32_t* bounds_host,
                                     int32_t* coef_host);
-HVLM_API int hvlm_resize_crop_u8(const uint8_t* src, int N, int H, int W, uint8_t* dst, int out_h, int out_w,
-                                 const int32_t* xbounds, const int32_t* xcoef, int xk, const int32_t* ybounds,
-                                 const int32_t* ycoef, int yk, void* stream);
+HVLM_API int hvlm_resize_crop_u8(const uint8_t* src, int N, const hvlm_resize_plan* plan_host, const int32_t* table,
+                                 uint8_t* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * helpers for the training-shaped variant

@@ -219,8 +219,12 @@ def _nccl_worker(rank, world, port, expect_path, q):
         ms = red.last_allreduce_ms()
         arch.check_deferred_status(host)
         exp = torch.load(expect_path)
-        relW = relmax(pm.weight.grad, exp["dW"])
-        relb = relmax(pm.bias.grad, exp["db"])
+        nW = pm.weight.numel()
+        relW = relmax(red.bucket[:nW].view(pm.weight.shape), exp["dW"])       # the all-reduced fp32 bucket
+        relb = relmax(red.bucket[nW:], exp["db"])
+        # .grad carries the same values in the parameters' dtype (bf16 here)
+        assert torch.equal(pm.weight.grad, red.bucket[:nW].view(pm.weight.shape).to(pm.weight.dtype))
+        assert torch.equal(pm.bias.grad, red.bucket[nW:].to(pm.bias.dtype))
         rel_local = relmax(local_w, exp["dW_rank"][rank])
         # every rank must end with the same bits
         chk = pm.weight.grad.float().sum().reshape(1).double()
