@@ -15,7 +15,6 @@
 
 namespace hvlm {
 
-constexpr int kMaxImgPerSample = 64;
 constexpr int kPad = INT_MIN;
 
 __global__ void splice_count_kernel(const int64_t* __restrict__ ids, int T, int32_t* __restrict__ counts) {
@@ -41,8 +40,7 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
                    float* __restrict__ hand_scale, int32_t* __restrict__ status,
                    int64_t* __restrict__ last_visual_end) {
     __shared__ int scan_smem[9];
-    __shared__ int img_pos[kMaxImgPerSample];
-    __shared__ int cum[kMaxImgPerSample + 1];   // cum[m] = rows added by the first m image tokens of this sample
+    __shared__ int chunk_pos[kPlanThreads];     // positions of the image tokens found in the current chunk of ids
     const int b = blockIdx.x;
     const int64_t* row = ids + static_cast<int64_t>(b) * T;
     int32_t* dst = src_index + static_cast<int64_t>(b) * L;
@@ -53,26 +51,22 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
     int slot0 = 0;
     for (int i = 0; i < b; ++i) slot0 += max(counts[i], 1);
     const int k_img = counts[b];
-    const int n_fill = min(k_img, kMaxImgPerSample);
     // rows of visual slot g: uniform Nv, or slot_offsets[g+1] - slot_offsets[g] when the caller hands in per-sample token
-    // blocks of different lengths (the list path of images_to_tokens, llava_arch.py:95-106)
+    // blocks of different lengths (the list path of images_to_tokens, llava_arch.py:95-106); slots past n_img have none
     auto nv_of = [&](int g) { return slot_offsets ? (g < n_img ? slot_offsets[g + 1] - slot_offsets[g] : 0) : Nv; };
-    if (threadIdx.x == 0) {
-        int c = 0;
-        for (int j = 0; j < n_fill; ++j) {
-            cum[j] = c;
-            c += nv_of(slot0 + j) - 1;
-        }
-        cum[n_fill] = c;
-    }
-    __syncthreads();
-    const int len = T + cum[n_fill];
-    int len0 = T;
-    for (int j = 0; j < min(counts[0], kMaxImgPerSample); ++j) len0 += nv_of(j) - 1;
+    // rows ADDED by the first m image tokens of the sample whose first slot is s0 (each token is replaced by its block):
+    // closed forms, so any number of image tokens per sample is fine (slot_offsets is itself a prefix sum)
+    auto cum_rows = [&](int s0, int m) {
+        if (!slot_offsets) return m * (Nv - 1);
+        const int g0 = min(s0, n_img), g1 = min(s0 + m, n_img);
+        return slot_offsets[g1] - slot_offsets[g0] - m;
+    };
+    const int len = T + cum_rows(slot0, k_img);
+    const int len0 = T + cum_rows(0, counts[0]);
     if (len > L) err |= HVLM_PLAN_ERR_LEN_OVERFLOW;
     // a sample without image token advances cur_image_idx but never indexes the features (llava_arch.py:127-135,
     // handsonvlm.py:234-245), so only samples that READ slots can overflow
-    if ((k_img > 0 && slot0 + k_img > n_img) || k_img > kMaxImgPerSample) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
+    if (k_img > 0 && slot0 + k_img > n_img) err |= HVLM_PLAN_ERR_IMG_OVERFLOW;
     if (len != len0) err |= HVLM_PLAN_NOT_UNIFORM;
 
     // defaults: padding + no hand code
@@ -81,44 +75,50 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
         hc[r] = -1;
     }
 
-    // text rows + image-token positions
+    // text rows, image-token positions, visual rows -- one 256-token chunk of the ids at a time
     int img_seen = 0;
+    int last_pos = -1, prev_pos = -1;            // positions of the last two image tokens seen so far (block-uniform)
     for (int p0 = 0; p0 < T; p0 += kPlanThreads) {
         const int p = p0 + threadIdx.x;
         const int64_t tok = p < T ? row[p] : 0;
         const int is_img = (p < T) && (tok == HVLM_IMAGE_TOKEN_INDEX);
         int total;
-        const int before = img_seen + block_excl_scan(is_img, &total, scan_smem);
+        const int local = block_excl_scan(is_img, &total, scan_smem);
+        const int before = img_seen + local;
         if (p < T) {
-            const int opos = p + cum[min(before, n_fill)];
             if (is_img) {
-                if (before < kMaxImgPerSample) img_pos[before] = p;
+                chunk_pos[local] = p;
             } else {
+                const int opos = p + cum_rows(slot0, before);
                 const bool bad = tok < 0 || tok >= vocab;   // never index the table out of bounds
                 if (bad) err |= HVLM_PLAN_ERR_BAD_ID;
-                if (opos < L) dst[opos] = bad ? kPad : p;
+                if (opos >= 0 && opos < L) dst[opos] = bad ? kPad : p;
             }
         }
+        __syncthreads();
+        for (int jj = 0; jj < total; ++jj) {
+            const int j = img_seen + jj;
+            const int o0 = chunk_pos[jj] + cum_rows(slot0, j);
+            const int g = slot0 + j;
+            const bool slot_ok = g < n_img;      // never plan a read past the visual tensor (error flagged above)
+            const int g0 = slot_offsets ? (slot_ok ? slot_offsets[g] : 0) : g * Nv;
+            const int nv = nv_of(g);
+            for (int r = threadIdx.x; r < nv; r += blockDim.x)
+                if (o0 + r >= 0 && o0 + r < L) dst[o0 + r] = slot_ok ? -(1 + g0 + r) : kPad;
+        }
+        if (total >= 2) prev_pos = chunk_pos[total - 2];
+        else if (total == 1) prev_pos = last_pos;
+        if (total >= 1) last_pos = chunk_pos[total - 1];
         img_seen += total;
-    }
-    __syncthreads();
-
-    // visual rows
-    for (int j = 0; j < n_fill; ++j) {
-        const int o0 = img_pos[j] + cum[j];
-        const int g0 = slot_offsets ? (slot0 + j < n_img ? slot_offsets[slot0 + j] : 0) : (slot0 + j) * Nv;
-        const int nv = nv_of(slot0 + j);
-        const bool slot_ok = slot0 + j < n_img;      // never plan a read past the visual tensor (error flagged above)
-        for (int r = threadIdx.x; r < nv; r += blockDim.x)
-            if (o0 + r < L) dst[o0 + r] = slot_ok ? -(1 + g0 + r) : kPad;
+        __syncthreads();                         // chunk_pos is rewritten by the next chunk
     }
 
     // hand positional embedding codes: only the tail segment (text after the LAST image token) of samples
     // that have an image token (handsonvlm.py:342-396)
     float scale = 0.f;
-    if (variant == HVLM_SPLICE_HANDSONVLM && hand_mode != 0 && k_img > 0 && k_img <= kMaxImgPerSample) {
-        const int tail0 = img_pos[k_img - 1] + 1;            // first tail position
-        const int shift = cum[k_img];                         // output row = p + shift
+    if (variant == HVLM_SPLICE_HANDSONVLM && hand_mode != 0 && k_img > 0) {
+        const int tail0 = last_pos + 1;                       // first tail position
+        const int shift = cum_rows(slot0, k_img);             // output row = p + shift
         int seen = 0;
         for (int p0 = tail0; p0 < T; p0 += kPlanThreads) {
             const int p = p0 + threadIdx.x;
@@ -126,7 +126,7 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
             int total;
             const int ord = seen + block_excl_scan(is_hand, &total, scan_smem);
             const int limit = hand_mode == 1 ? 4 : n_hand_points;
-            if (is_hand && ord < limit && p + shift < L) hc[p + shift] = static_cast<int8_t>(ord);
+            if (is_hand && ord < limit && p + shift >= 0 && p + shift < L) hc[p + shift] = static_cast<int8_t>(ord);
             seen += total;
         }
         __syncthreads();
@@ -134,7 +134,8 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
             if (seen > 4) err |= HVLM_PLAN_ERR_HAND_COUNT;
             scale = static_cast<float>(seen) / 4.0f;
             // zero.scatter(0, idx, emb) with idx padded by 0: row 0 of the tail receives emb[3] (last writer)
-            if (seen > 0 && seen < 4 && tail0 < T && threadIdx.x == 0 && tail0 + shift < L) hc[tail0 + shift] = 3;
+            if (seen > 0 && seen < 4 && tail0 < T && threadIdx.x == 0 && tail0 + shift >= 0 && tail0 + shift < L)
+                hc[tail0 + shift] = 3;
         } else {
             if (tail0 < T && seen != n_hand_points) err |= HVLM_PLAN_ERR_HAND_COUNT;
             scale = 1.0f;
@@ -147,11 +148,11 @@ splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ 
         // for every image token of every sample, where image_token_start indexes the ids that are LEFT after the previous
         // image token was cut off.  The value that survives is the one of the last image token of the last sample that
         // has one: only that sample's CTA writes.
-        if (last_visual_end && k_img > 0 && k_img <= kMaxImgPerSample) {
+        if (last_visual_end && k_img > 0) {
             bool last = true;
             for (int i = b + 1; i < B; ++i) last = last && counts[i] == 0;
             if (last) {
-                const int rel = img_pos[k_img - 1] - (k_img > 1 ? img_pos[k_img - 2] + 1 : 0);
+                const int rel = last_pos - (k_img > 1 ? prev_pos + 1 : 0);
                 *last_visual_end = static_cast<int64_t>(rel) + nv_of(slot0 + k_img - 1);
             }
         }

@@ -208,8 +208,7 @@ HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok
  *                             (handsonvlm.py:288) = position of the last image token of the last sample that has one,
  *                             relative to the ids left after the previous image token, + its number of visual rows.
  *                             Left untouched when no sample has an image token.
- * Limit: at most 64 image tokens per sample (HVLM_PLAN_ERR_IMG_OVERFLOW beyond; the reference has no limit, its
- *        collators emit one).
+ * Any number of image tokens per sample (round 1 capped it at 64).
  * ---------------------------------------------------------------------------------------------- */
 /* OR-able into `variant` of hvlm_splice_plan / hvlm_splice_fwd: the `tune_mm_mlp_adapter && mm_use_im_start_end` branch of
  * llava_arch.py:146-161,172-173 -- the embeddings are the same rows, but the token right after an image token (<im_end>)

@@ -521,3 +521,29 @@ def test_static_splice_contract_violation_is_reported():
     with pytest.raises(RuntimeError, match="static_splice"):
         run(ids)                                                           # the NEXT call's poll reports it
     arch.check_deferred_status(host)
+
+
+def test_splice_many_image_tokens_per_sample():
+    """Round 1 capped a sample at 64 image tokens; the plan kernel now uses closed-form row offsets: 150 image tokens in one
+    sample, spread over two 256-token chunks of the ids, against the oracle (both variants, ints + rows bit-exact)."""
+    D, Nv, T, B = 64, 3, 600, 2
+    g = torch.Generator().manual_seed(77)
+    ids = torch.randint(1, 32000, (B, T), generator=g, dtype=torch.int64)
+    pos = torch.randperm(T - 2, generator=g)[:150].sort().values + 1
+    ids[0, pos] = -200
+    ids[1, 300] = -200
+    labels = ids.clone()
+    mask = torch.ones(B, T, dtype=torch.bool)
+    vis = synth.gen("many.vis", (151, Nv, D), 1.0, 3)
+    table = synth.gen("many.tab", (synth.VOCAB, D), 1.0, 3)
+    host = types.SimpleNamespace(
+        get_model=lambda: types.SimpleNamespace(embed_tokens=types.SimpleNamespace(weight=table.to(DEV))),
+        config=types.SimpleNamespace())
+    for variant, name in ((L.SPLICE_LLAVA, "llava"), (L.SPLICE_HANDSONVLM, "handsonvlm")):
+        lve = torch.full((), -1, dtype=torch.int64, device=DEV)
+        m2, e2, l2 = arch.splice_tokens(host, variant, ids.to(DEV), mask.to(DEV), labels.to(DEV), vis.to(DEV), None, None,
+                                        True, last_visual_end=lve)
+        rm, re_, rl = restate.splice(ids, mask, labels, vis, table, name, is_evaluate=True)
+        assert e2.shape == re_.shape == (B, T + 150 * (Nv - 1), D)
+        assert torch.equal(e2.cpu(), re_) and torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm), name
+        assert int(lve) == restate.last_visual_token_index(ids, Nv)
