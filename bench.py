@@ -645,13 +645,13 @@ def run_train(c, args, D, B, steps, warmup):
             import torch.distributed as dist
             hd.barrier()
             for _ in range(3):
-                dist.all_reduce(red.bucket, op=dist.ReduceOp.AVG)
+                dist.all_reduce(red.bucket, op=dist.ReduceOp.AVG, group=red.group)
             torch.cuda.synchronize()
             hd.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(20):
-                dist.all_reduce(red.bucket, op=dist.ReduceOp.AVG)
+                dist.all_reduce(red.bucket, op=dist.ReduceOp.AVG, group=red.group)
             e1.record()
             torch.cuda.synchronize()
             iso_ms = hd.max_over_ranks(e0.elapsed_time(e1) / 20, dev)

@@ -606,6 +606,12 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
     }();
     if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
         return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
+    // HVLM_QKV_EPI_GROUPS=2: the same second epilogue group for the QKV GEMM (A/B runs; see DESIGN.md for the outcome)
+    static const bool qkv_two = []() {
+        const char* e = getenv("HVLM_QKV_EPI_GROUPS");
+        return e && e[0] == '2';
+    }();
+    if (qkv_two && epi == EPI_QKV_HM) return launch_two<EPI_QKV_HM, false, 2>(A, B, M, N, K, ep, s);
     switch (epi) {
         case EPI_BIAS_BF16: return launch_two<EPI_BIAS_BF16>(A, B, M, N, K, ep, s);
         case EPI_BIAS_F32: return launch_two<EPI_BIAS_F32>(A, B, M, N, K, ep, s);

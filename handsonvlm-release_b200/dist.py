@@ -84,6 +84,38 @@ def allreduce_projector_grads(projector: torch.nn.Module, group=None, async_op: 
     return None
 
 
+_own_group = None
+
+
+def _dedicated_nccl_group():
+    """The collective runs on a side stream WHILE the next step's ViT forward runs on the main stream, and that forward is
+    a chain of persistent kernels that own every SM (one 225 KB CTA per SM): an NCCL kernel that is resident and spinning
+    on slower ranks takes SMs away from them.  The reducer therefore uses its own communicator, created with
+    ncclConfig ctaPolicy = EFFICIENCY on a high-priority stream.  Measured on one 8-GPU B200 box, training-shaped variant,
+    same box back to back (profiles/r2_train_nccl_sweep.txt; 8-GPU step / collective alone / collective inside the step):
+        ctaPolicy EFFICIENCY      60.08 ms  0.086 ms  3.7 ms   (0.993 of 8x the 1-GPU rate)   <- default
+        default config            60.13 ms  0.085 ms  5.5 ms   (0.992)
+        max 8 / 2 / 1 CTAs        60.26 / 60.56 / 60.88 ms; 0.22 / 0.75 / 1.47 ms alone       (0.990 / 0.985 / 0.980)
+    i.e. capping the CTAs only makes the collective slower (16.8 MB is latency-bound at any width) and holds its SMs longer.
+    HVLM_NCCL_CTA_POLICY (default 1), HVLM_NCCL_MAX_CTAS (default 0 = unset), HVLM_NCCL_HIGH_PRIO (default 1) for A/B runs.
+    Collective call: every rank constructs its reducer at the same point.  Returns None (default group) off NCCL."""
+    global _own_group
+    if not dist.is_initialized() or dist.get_world_size() == 1 or dist.get_backend() != "nccl":
+        return None
+    if _own_group is None:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = os.environ.get("HVLM_NCCL_HIGH_PRIO", "1") != "0"
+        max_ctas = int(os.environ.get("HVLM_NCCL_MAX_CTAS", "0"))
+        if max_ctas > 0:
+            opts.config.max_ctas = max_ctas
+            opts.config.min_ctas = 1
+        pol = int(os.environ.get("HVLM_NCCL_CTA_POLICY", "1"))      # NCCL_CTA_POLICY_EFFICIENCY
+        if pol >= 0:
+            opts.config.cta_policy = pol
+        _own_group = dist.new_group(backend="nccl", pg_options=opts)
+    return _own_group
+
+
 class ProjectorGradReducer:
     """The training-shaped variant's only exchange step (the reference leaves it to ZeRO's reduce,
     scripts/zero3.json:16-27): mean all-reduce of ``mm_projector.{weight,bias}.grad`` over NCCL / NVLink.
@@ -102,6 +134,8 @@ class ProjectorGradReducer:
 
     def __init__(self, projector: torch.nn.Module, group=None, use_sink: bool = True):
         self.projector = projector
+        if group is None:
+            group = _dedicated_nccl_group()
         self.group = group
         self.params = [projector.weight] + ([projector.bias] if getattr(projector, "bias", None) is not None else [])
         self.nW, self.nb = _flat_sizes(projector)
