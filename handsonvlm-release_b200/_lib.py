@@ -83,6 +83,7 @@ SIGNATURES = {
     "hvlm_resize_plan_host": (i32, [i32, i32, i32, i32, p]),
     "hvlm_resize_tables_host": (i32, [p, C.POINTER(C.c_int32)]),
     "hvlm_resize_crop_u8": (i32, [p, i32, p, p, p, p]),
+    "hvlm_pad_square_u8": (i32, [p, i32, i32, i32, p, i32, i32, i32, p]),
     "hvlm_transpose_to_bf16": (i32, [p, i32, p, i32, i32, i32, p]),
     "hvlm_colsum": (i32, [p, i32, p, i32, i32, p]),
     "hvlm_launch_count": (C.c_uint64, []),

@@ -216,6 +216,34 @@ resize_crop_u8_big_kernel(const uint8_t* __restrict__ src, const __grid_constant
     }
 }
 
+// expand2square (hoi_forecast/dataset/video_utils.py:13-25, the `image_aspect_ratio == 'pad'` branch of load_image :30-31):
+// the frame is pasted in the middle of a square canvas of the background colour.  Thread = 4 output bytes.
+__global__ void __launch_bounds__(256)
+pad_square_u8_kernel(const uint8_t* __restrict__ src, int H, int W, uint8_t* __restrict__ dst, int S, int x0, int y0,
+                     uint32_t bg /* r | g << 8 | b << 16 */) {
+    const int n = blockIdx.z, y = blockIdx.y;
+    const size_t row_bytes = static_cast<size_t>(S) * 3;
+    uint8_t* out = dst + (static_cast<size_t>(n) * S + y) * row_bytes;
+    const int ys = y - y0;
+    const uint8_t* in = (ys >= 0 && ys < H) ? src + (static_cast<size_t>(n) * H + ys) * W * 3 : nullptr;
+    const int lo = x0 * 3, hi = (x0 + W) * 3;
+    for (int b4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; b4 < static_cast<int>(row_bytes); b4 += gridDim.x * blockDim.x * 4) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = b4 + j;
+            uint32_t v = (bg >> (8 * (b % 3))) & 0xffu;
+            if (in != nullptr && b >= lo && b < hi) v = in[b - lo];
+            w |= v << (8 * j);
+        }
+        if (b4 + 4 <= static_cast<int>(row_bytes)) {
+            *reinterpret_cast<uint32_t*>(out + b4) = w;      // S*3 bytes per row; rows are 4-byte aligned when S % 4 == 0
+        } else {
+            for (int j = 0; b4 + j < static_cast<int>(row_bytes); ++j) out[b4 + j] = static_cast<uint8_t>(w >> (8 * j));
+        }
+    }
+}
+
 static inline int kmax_of(const hvlm_resize_plan& p) { return p.xk <= 8 ? 8 : (p.xk <= 12 ? 12 : 24); }
 // staged row = 15 bytes of alignment slack + the window + the aligned-word over-read of the last column (3*KMAX + 8 bytes)
 static inline int src_pitch_of(const hvlm_resize_plan& p) {
@@ -350,4 +378,22 @@ extern "C" int hvlm_resize_crop_u8(const uint8_t* src, int N, const hvlm_resize_
         return HVLM_ERR_CUDA;
     resize_crop_u8_big_kernel<<<grid, kThreads, big, s>>>(src, p, table, dst);
     return check_last("resize_crop_u8_big");
+}
+
+extern "C" int hvlm_pad_square_u8(const uint8_t* src, int N, int H, int W, uint8_t* dst, int bg_r, int bg_g, int bg_b,
+                                  void* stream) {
+    using namespace hvlm;
+    if (!src || !dst || N <= 0 || H <= 0 || W <= 0) return HVLM_ERR_BAD_ARG;
+    if ((bg_r | bg_g | bg_b) < 0 || bg_r > 255 || bg_g > 255 || bg_b > 255) return HVLM_ERR_BAD_ARG;
+    const int S = H > W ? H : W;
+    if ((S % 4) != 0 || (reinterpret_cast<uintptr_t>(dst) & 3u) != 0) return HVLM_ERR_ALIGN;   // 32-bit row stores
+    if (S > 65535 || N > 65535) return HVLM_ERR_BAD_SHAPE;
+    const int x0 = W >= H ? 0 : (H - W) / 2, y0 = W > H ? (W - H) / 2 : 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StageTimer st(HVLM_STAGE_IM2COL, s);
+    const int gx = (S * 3 / 4 + 255) / 256;
+    resize::pad_square_u8_kernel<<<dim3(gx, S, N), 256, 0, s>>>(src, H, W, dst, S, x0, y0,
+                                                               static_cast<uint32_t>(bg_r) | (static_cast<uint32_t>(bg_g) << 8) |
+                                                                   (static_cast<uint32_t>(bg_b) << 16));
+    return check_last("pad_square_u8");
 }

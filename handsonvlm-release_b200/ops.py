@@ -770,3 +770,21 @@ def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor
     out = torch.empty(N, size, size, 3, dtype=torch.uint8, device=frames.device)
     L.check(L.lib().hvlm_resize_crop_u8(_p(frames), N, C.byref(plan), _p(table), _p(out), _stream()), "hvlm_resize_crop_u8")
     return out
+
+
+def pad_square_u8(frames: torch.Tensor, background=(122, 116, 104)) -> torch.Tensor:
+    """expand2square (hoi_forecast/dataset/video_utils.py:13-25): uint8 [N,H,W,3] -> [N,S,S,3], S = max(H,W), the frame
+    centred on a canvas of ``background`` (default: int(255 * OPENAI_CLIP_MEAN), what load_image passes for 'pad')."""
+    _need_cuda(frames)
+    ensure_device()
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError(f"expected uint8 frames [N,H,W,3], got {frames.dtype} {tuple(frames.shape)}")
+    frames = frames.contiguous()
+    N, H, W, _ = frames.shape
+    if H == W:
+        return frames
+    S = max(H, W)
+    out = torch.empty(N, S, S, 3, dtype=torch.uint8, device=frames.device)
+    r, g, b = (int(v) for v in background)
+    L.check(L.lib().hvlm_pad_square_u8(_p(frames), N, H, W, _p(out), r, g, b, _stream()), "hvlm_pad_square_u8")
+    return out

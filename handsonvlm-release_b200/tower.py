@@ -124,11 +124,17 @@ class CLIPVisionTower(nn.Module):
         b = self.weight_blob[int(y.b_fc2): int(y.b_fc2) + 1024 * 4].view(torch.float32)
         return w, b
 
-    def preprocess_u8(self, frames: torch.Tensor) -> torch.Tensor:
-        """Decoded frames uint8 [N,H,W,3] on the device -> uint8 [N,224,224,3]: this tower's ``image_processor`` resize +
-        centre crop as one kernel, bit-identical to PIL (hoi_forecast/dataset/video_utils.py:28-53 does it per frame on the
-        CPU).  The result goes straight into ``forward`` / ``forward_hidden`` (rescale + normalise are fused there)."""
-        return ops.resize_center_crop_u8(frames.to(self.device), _CFG["image_size"])
+    def preprocess_u8(self, frames: torch.Tensor, image_aspect_ratio: str = "square") -> torch.Tensor:
+        """Decoded frames uint8 [N,H,W,3] on the device -> uint8 [N,224,224,3]: ``load_image`` of
+        hoi_forecast/dataset/video_utils.py:28-53 without the CPU -- the optional ``image_aspect_ratio == 'pad'`` canvas
+        (expand2square with int(255 * image_mean), :30-31) and this tower's ``image_processor`` resize + centre crop as
+        kernels, bit-identical to PIL.  The result goes straight into ``forward`` / ``forward_hidden`` (rescale + normalise
+        are fused there)."""
+        frames = frames.to(self.device)
+        if image_aspect_ratio == "pad":
+            mean = getattr(getattr(self, "image_processor", None), "image_mean", None) or ops.CLIP_MEAN
+            frames = ops.pad_square_u8(frames, tuple(int(x * 255) for x in mean))
+        return ops.resize_center_crop_u8(frames, _CFG["image_size"])
 
     @torch.no_grad()
     def forward(self, images):

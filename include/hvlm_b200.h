@@ -350,6 +350,11 @@ HVLM_API int hvlm_resize_table_host(int in_size, int out_size, int crop0, int cr
                                     int32_t* coef_host);
 HVLM_API int hvlm_resize_crop_u8(const uint8_t* src, int N, const hvlm_resize_plan* plan_host, const int32_t* table,
                                  uint8_t* dst, void* stream);
+/* expand2square (hoi_forecast/dataset/video_utils.py:13-25), the `image_aspect_ratio == 'pad'` branch of load_image
+ * (:30-31): src uint8 [N,H,W,3] pasted in the middle of dst uint8 [N,S,S,3], S = max(H,W) (S % 4 == 0), filled with the
+ * background colour (the reference passes tuple(int(255 * m) for m in processor.image_mean) = (122, 116, 104)). */
+HVLM_API int hvlm_pad_square_u8(const uint8_t* src, int N, int H, int W, uint8_t* dst, int bg_r, int bg_g, int bg_b,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * helpers for the training-shaped variant

@@ -385,6 +385,29 @@ def golden_traj(ns):
         save("traj_mlp_infer", out=mlp.inference(pred_hand_embeddings=emb))
 
 
+def golden_preprocess(ns):
+    """hoi_forecast/dataset/video_utils.py:28-53 (load_image) on in-memory frames: the reference's own expand2square for the
+    'pad' branch, then `processor.preprocess` with the PIL-backed CLIPImageProcessor (what transformers==4.31.0 runs)."""
+    import importlib.util
+    import transformers
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("ref_video_utils", os.path.join(ref_shim.REF, "hoi_forecast/dataset/video_utils.py"))
+    vu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vu)
+    proc = getattr(transformers.models.clip, "CLIPImageProcessorPil", transformers.CLIPImageProcessor)()
+    rng = np.random.RandomState(77)
+    for name, (H, W) in (("landscape", (128, 228)), ("portrait", (150, 100))):
+        frame = rng.randint(0, 256, (H, W, 3), dtype=np.uint8)
+        yy, xx = np.mgrid[0:H, 0:W]
+        frame[..., 1] = ((xx * 3 + yy * 5) % 256).astype(np.uint8)             # some structure next to the noise
+        img = Image.fromarray(frame)
+        sq = proc.preprocess(img, return_tensors="pt")["pixel_values"][0]
+        padded = vu.expand2square(img, tuple(int(x * 255) for x in proc.image_mean))
+        pd = proc.preprocess(padded, return_tensors="pt")["pixel_values"][0]
+        save(f"preprocess_{name}", frame=frame, square=sq[:, ::2, ::2].contiguous(), pad=pd[:, ::2, ::2].contiguous(),
+             padded_size=np.array(padded.size))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -405,6 +428,7 @@ def main():
     golden_splice_hvlm_im_start_end(ns)
     golden_splice_llava_list(ns)
     golden_vit_full(ns)
+    golden_preprocess(ns)
 
 
 if __name__ == "__main__":

@@ -549,6 +549,25 @@ def clip_resize_center_crop_u8(frames: np.ndarray, size: int = 224) -> np.ndarra
     return np.ascontiguousarray(out[:, top:top + size, left:left + size])
 
 
+def expand2square_u8(frames: np.ndarray, background=None) -> np.ndarray:
+    """hoi_forecast/dataset/video_utils.py:13-25 (the `image_aspect_ratio == 'pad'` branch of load_image, :30-31):
+    paste at (0, (w-h)//2) for landscape, ((h-w)//2, 0) for portrait, on a canvas of int(255 * image_mean)."""
+    N, H, W, _ = frames.shape
+    if H == W:
+        return frames
+    bg = tuple(int(x * 255) for x in CLIP_MEAN) if background is None else background
+    S = max(H, W)
+    out = np.empty((N, S, S, 3), np.uint8)
+    out[...] = np.asarray(bg, np.uint8)
+    if W > H:
+        y0 = (W - H) // 2
+        out[:, y0:y0 + H, :, :] = frames
+    else:
+        x0 = (H - W) // 2
+        out[:, :, x0:x0 + W, :] = frames
+    return out
+
+
 def clip_normalize_u8(frames: np.ndarray) -> torch.Tensor:
     """uint8 [N,h,w,3] -> float32 [N,3,h,w]: rescale 1/255 + CLIP mean/std normalisation."""
     x = torch.from_numpy(frames).float().mul(1.0 / 255.0)

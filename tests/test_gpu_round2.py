@@ -416,6 +416,19 @@ def test_resize_center_crop_u8_bit_exact(H, W):
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("H,W", [(256, 456), (300, 200), (128, 228), (224, 224)])
+def test_pad_square_and_resize_bit_exact(tower_hf, H, W):
+    """The `image_aspect_ratio == 'pad'` branch of load_image (video_utils.py:30-31): expand2square on the device, then the
+    resize -- against the oracle (pinned to the reference's own expand2square + PIL by the preprocess_* fixtures)."""
+    tw, _ = tower_hf
+    frames = np.random.RandomState(H * 7 + W).randint(0, 256, (2, H, W, 3), dtype=np.uint8)
+    ref_sq = restate.expand2square_u8(frames)
+    out_sq = ops.pad_square_u8(torch.from_numpy(frames).to(DEV))
+    assert np.array_equal(out_sq.cpu().numpy(), ref_sq)
+    out = tw.preprocess_u8(torch.from_numpy(frames).to(DEV), image_aspect_ratio="pad")
+    assert np.array_equal(out.cpu().numpy(), restate.clip_resize_center_crop_u8(ref_sq))
+
+
 def test_decoded_frames_to_features(tower_hf):
     """Decoded EPIC-KITCHENS-sized frames (256 x 456 uint8) -> preprocess_u8 (resize + crop kernel) -> tower (rescale +
     normalise fused into the patch extraction) against the oracle's processor + ViT."""

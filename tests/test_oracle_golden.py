@@ -352,3 +352,18 @@ def test_frame_dedup_restatement():
     neg0 = torch.zeros(2, 4)
     neg0[1] = -0.0                       # byte-wise comparison: +0 and -0 are different frames
     assert restate.frame_dedup(neg0)[1].tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("name", ["landscape", "portrait"])
+def test_preprocess_matches_reference_fixture(golden, name):
+    """load_image of hoi_forecast/dataset/video_utils.py:28-53, both `image_aspect_ratio` branches, frozen from the
+    reference's own expand2square + the PIL-backed CLIPImageProcessor: the oracle's integer restatement reproduces the
+    float pixels (rescale + normalise rounding only)."""
+    g = golden(f"preprocess_{name}")
+    frame = g["frame"][None]
+    sq = restate.clip_normalize_u8(restate.clip_resize_center_crop_u8(frame))[0]
+    assert float((sq[:, ::2, ::2] - T(g["square"])).abs().max()) <= 1e-6
+    padded = restate.expand2square_u8(frame)
+    assert tuple(padded.shape[1:3][::-1]) == tuple(int(v) for v in g["padded_size"])
+    pd = restate.clip_normalize_u8(restate.clip_resize_center_crop_u8(padded))[0]
+    assert float((pd[:, ::2, ::2] - T(g["pad"])).abs().max()) <= 1e-6
