@@ -560,3 +560,47 @@ def test_splice_many_image_tokens_per_sample():
         assert e2.shape == re_.shape == (B, T + 150 * (Nv - 1), D)
         assert torch.equal(e2.cpu(), re_) and torch.equal(l2.cpu(), rl) and torch.equal(m2.cpu(), rm), name
         assert int(lve) == restate.last_visual_token_index(ids, Nv)
+
+
+_OPTIN_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import hvlm_b200
+from hvlm_b200 import ops
+from oracle import synth
+dev = "cuda:0"
+def relmax(a, b):
+    return float((a.float().cpu() - b.float().cpu()).abs().max() / b.float().cpu().abs().max())
+for (M, N, K) in [(300, 1024, 1024), (2571, 1024, 1024), (25700, 1024, 1024), (777, 256, 72), (1025, 512, 4096)]:
+    a = synth.gen("o.A", (M, K), 1.0, 1).to(torch.bfloat16).to(dev)
+    w = synth.gen("o.W", (N, K), K ** -0.5, 1).to(torch.bfloat16).to(dev)
+    bias = synth.gen("o.b", (N,), 0.5, 1).to(dev)
+    res = synth.gen("o.r", (M, N), 1.0, 2).to(dev)
+    ref = a.float() @ w.float().t() + bias + res
+    r2 = res.clone()
+    ops.gemm(a, w, bias, epilogue="residual", resid=r2, out=r2)
+    assert relmax(r2, ref) <= 2e-5, (M, N, K, relmax(r2, ref))
+    r3 = res.clone()
+    ops.gemm(a, w, bias, epilogue="residual", resid=r3, out=r3)
+    assert torch.equal(r2, r3)
+y = synth.gen("o.y", (3 * 257, 1024), 1.0, 3).to(torch.bfloat16).to(dev)
+wq = synth.gen("o.wq", (3072, 1024), 1024 ** -0.5, 3).to(torch.bfloat16).to(dev)
+bq = synth.gen("o.bq", (3072,), 0.1, 3).to(dev)
+qkv = ops.vit_qkv(y, wq, bq, 3)                                  # [48, M, 64] column-block-major
+ref = (y.float() @ wq.float().t() + bq).reshape(3 * 257, 48, 64).permute(1, 0, 2)
+assert relmax(qkv, ref) <= 5e-3
+print("optin ok")
+'''
+
+
+def test_opt_in_kernel_variants_stay_correct(tmp_path):
+    """The experiment switches that are off by default (residual-load epilogue, second epilogue group for the QKV GEMM) are
+    read once per process, so they are exercised in a child process: same tolerances as the default kernels."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "optin.py"
+    script.write_text(_OPTIN_SCRIPT)
+    env = dict(os.environ, HVLM_RESID_LOAD_MAXK="4096", HVLM_QKV_EPI_GROUPS="2")
+    r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "optin ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
