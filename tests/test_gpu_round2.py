@@ -604,3 +604,41 @@ def test_opt_in_kernel_variants_stay_correct(tmp_path):
     env = dict(os.environ, HVLM_RESID_LOAD_MAXK="4096", HVLM_QKV_EPI_GROUPS="2")
     r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "optin ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_frame_dedup_randomised():
+    """Seeded fuzz: random duplicate patterns, frame sizes (16-byte multiples), element types; frame map / rep / count against
+    the oracle, and gather_rows(rep) reproduces every frame through the map."""
+    rng = np.random.RandomState(11)
+    for case in range(20):
+        n = int(rng.choice([2, 3, 17, 64, 100, 257, 1000]))
+        u = int(rng.randint(1, n + 1))
+        words = int(rng.choice([4, 12, 100, 1029, 37632]))            # 16-byte vectors per frame: x4 int32 words
+        base = torch.from_numpy(rng.randint(-2 ** 31, 2 ** 31 - 1, (u, words * 4), dtype=np.int64).astype(np.int32))
+        if case % 3 == 0 and u > 1:
+            base[1] = base[0]
+            base[1, -1] ^= 1                                           # differs from frame 0 in its very last bit only
+        pick = torch.from_numpy(rng.randint(0, u, n))
+        frames = base[pick].contiguous()
+        if case % 2:
+            frames = frames.view(torch.uint8)
+        fr, rr = restate.frame_dedup(frames)
+        fm, rep, nu = ops.frame_dedup(frames.to(DEV))
+        U = int(nu.item())
+        assert U == rr.numel(), (case, U, rr.numel())
+        assert torch.equal(fm.cpu(), fr) and torch.equal(rep[:U].cpu(), rr), case
+        back = ops.gather_rows(frames.to(DEV), rep, U)[fm.long()]
+        assert torch.equal(back.cpu(), frames), case
+
+
+def test_resize_center_crop_randomised_geometries():
+    """Seeded fuzz over source geometries (portrait / landscape, mild to strong down-scaling, up-scaling, odd sizes whose
+    rows are not 4- or 16-byte multiples): bit-exact against the oracle (pinned to PIL)."""
+    rng = np.random.RandomState(12)
+    for case in range(14):
+        H = int(rng.randint(120, 760))
+        W = int(rng.randint(120, 1100))
+        frames = rng.randint(0, 256, (2, H, W, 3), dtype=np.uint8)
+        ref = restate.clip_resize_center_crop_u8(frames)
+        out = ops.resize_center_crop_u8(torch.from_numpy(frames).to(DEV))
+        assert np.array_equal(out.cpu().numpy(), ref), (case, H, W)
