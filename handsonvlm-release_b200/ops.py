@@ -703,6 +703,7 @@ def hand_gather_step(hidden_last: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # frame de-duplication and the uint8 resize / centre crop in front of the tower
 # ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("hvlm::frame_dedup", mutates_args=())
 def frame_dedup(frames: torch.Tensor, capacity: int = 0) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """frames [N, ...] (any dtype, contiguous; bytes per frame % 16 == 0) -> (frame_map int32 [N], rep int32 [N],
     n_unique int32 [1]), all on the device, no host sync.  ``rep[:n_unique]`` lists the first occurrence of every distinct
@@ -724,6 +725,14 @@ def frame_dedup(frames: torch.Tensor, capacity: int = 0) -> Tuple[torch.Tensor, 
     return frame_map, rep, n_unique
 
 
+@frame_dedup.register_fake
+def _(frames, capacity=0):
+    n = frames.shape[0]
+    return (frames.new_empty(n, dtype=torch.int32), frames.new_empty(n, dtype=torch.int32),
+            frames.new_empty(1, dtype=torch.int32))
+
+
+@torch.library.custom_op("hvlm::gather_rows", mutates_args=())
 def gather_rows(src: torch.Tensor, idx: torch.Tensor, n_out: Optional[int] = None) -> torch.Tensor:
     """out[i] = src[idx[i]] for i < n_out (idx int32 on the device; n_out is a HOST number, default len(idx))."""
     _need_cuda(src, idx)
@@ -736,6 +745,11 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, n_out: Optional[int] = Non
     out = torch.empty((n_out,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     L.check(L.lib().hvlm_gather_rows(_p(src), rb, src.shape[0], _p(idx), n_out, _p(out), _stream()), "hvlm_gather_rows")
     return out
+
+
+@gather_rows.register_fake
+def _(src, idx, n_out=None):
+    return src.new_empty((idx.numel() if n_out is None else n_out,) + tuple(src.shape[1:]))
 
 
 _resize_plans: dict = {}
@@ -757,6 +771,7 @@ def resize_plan(H: int, W: int, size: int, device):
     return hit
 
 
+@torch.library.custom_op("hvlm::resize_center_crop_u8", mutates_args=())
 def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor:
     """Decoded frames uint8 [N,H,W,3] -> uint8 [N,size,size,3]: CLIPImageProcessor's resize (shortest edge -> size, PIL
     BICUBIC, bit-identical to Pillow) + centre crop, one launch; feed the result to the tower's uint8 path."""
@@ -770,6 +785,11 @@ def resize_center_crop_u8(frames: torch.Tensor, size: int = 224) -> torch.Tensor
     out = torch.empty(N, size, size, 3, dtype=torch.uint8, device=frames.device)
     L.check(L.lib().hvlm_resize_crop_u8(_p(frames), N, C.byref(plan), _p(table), _p(out), _stream()), "hvlm_resize_crop_u8")
     return out
+
+
+@resize_center_crop_u8.register_fake
+def _(frames, size=224):
+    return frames.new_empty(frames.shape[0], size, size, 3)
 
 
 def pad_square_u8(frames: torch.Tensor, background=(122, 116, 104)) -> torch.Tensor:

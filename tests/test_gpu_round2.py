@@ -642,3 +642,73 @@ def test_resize_center_crop_randomised_geometries():
         ref = restate.clip_resize_center_crop_u8(frames)
         out = ops.resize_center_crop_u8(torch.from_numpy(frames).to(DEV))
         assert np.array_equal(out.cpu().numpy(), ref), (case, H, W)
+
+
+def test_training_shaped_backward_config5_size(tower_hf):
+    """BASELINE configs[4] at full per-GPU size: 4 clips x 100 frames, D = 4096, fwd + bwd through pool / projector / splice /
+    gather with upstream gradients; projector dW / db (wgrad GEMM K = 4 x 356 = 1424 pooled rows, through the reducer's
+    flat fp32 bucket) against the fp32 oracle's autograd formulas."""
+    tw, sd = tower_hf
+    D, t, B = 4096, 100, 4
+    proj, ps = projector(D)
+    emb = torch.nn.Embedding(synth.VOCAB, D)
+    emb.weight.data.copy_(synth.embed_table(D))
+    emb.weight.requires_grad_(False)
+    host = make_host(tw, proj, emb.to(torch.bfloat16), video_cfg(hvlm_static_splice=True), B)
+    pm = host.model.mm_projector
+    red = hd.ProjectorGradReducer(pm)
+    try:
+        g = torch.Generator(device=DEV)
+        g.manual_seed(55)
+        px = torch.randn(B, t, 3, 224, 224, device=DEV, generator=g).to(torch.bfloat16)
+        ids, mask, labels, fh, fv = synth.prompt_handsonvlm(B=B, seed=55)
+        Lout = ids.shape[1] + 355
+        de = synth.gen("c5.de", (B, Lout, D), 1.0, 55).to(torch.bfloat16)
+        dg = synth.gen("c5.dg", (B, 2, 4, D // 2), 1.0, 55).to(torch.bfloat16)
+        r = host.prepare_inputs_labels_for_multimodal(ids.to(DEV), mask.to(DEV), None, labels.to(DEV), px,
+                                                      future_hands=fh.to(DEV), future_valid=fv.to(DEV), is_evaluate=False)
+        gout, _ = host.gather_hand_traj_states(r[3], r[4], strict=False)
+        torch.autograd.backward([r[3], gout], [de.to(DEV), dg.to(DEV)])
+        arch.check_deferred_status(host)
+        nW = pm.weight.numel()
+        dW_gpu, db_gpu = red.bucket[:nW].view(pm.weight.shape).clone(), red.bucket[nW:].clone()
+    finally:
+        red.close()
+    # oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, _, rl = restate.splice(ids, mask, labels, torch.zeros(B, 356, 8), torch.zeros(synth.VOCAB, 8), "handsonvlm",
+                              future_hands=fh)
+    _, _, rows = restate.gather_hand_traj(torch.zeros(B, Lout, D), rl)
+    d_emb = de.float() + restate.gather_hand_traj_backward(dg.float(), rows, Lout)
+    d_vis, _ = restate.splice_backward(d_emb, ids, 356, B, synth.VOCAB)
+    pooled = []
+    for b in range(B):                                          # one clip at a time: bounded host memory
+        feats = restate.tower_forward(px[b].float().cpu(), sd, -2).reshape(1, t, 256, 1024)
+        pooled.append(restate.pool_tokens(feats, "temporal_spatial_pool"))
+    dW, db = restate.projector_grads(torch.cat(pooled, 0), d_vis)
+    assert relmax(dW_gpu, dW) <= TOL_BF16 and relmax(db_gpu, db) <= 1e-4
+    assert relmax(pm.weight.grad, dW) <= TOL_BF16
+
+
+def test_bench_line_has_the_contract_keys(tmp_path):
+    """`python bench.py` (forward-only mode, 3 steps) on this GPU: one JSON line with the driver's keys, a roofline object
+    whose fraction is achieved / peak, an e2e object with declared copy sizes, a non-zero launch count and a clock record."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--mode", "forward", "--steps", "3", "--warmup", "3",
+                        "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert k in line, k
+    assert line["unit"] == "frames/s" and line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] >= 3
+    assert line["value"] > 1000 and abs(line["value"] - 100 / (line["ms_per_step"] / 1e3)) / line["value"] < 1e-3
+    assert line["gpu_launches"] == 3 * 171
+    rf = line["roofline"]
+    assert rf["bound"] == "tensor" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3 and 0.3 < rf["frac"] < 1.2
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] == 100 * 3 * 224 * 224 * 4 + 62 * (8 + 1 + 8) + 2 * 4 * 2 * 4 + 2 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] > 1000 and "workload" in line["config"] and line["config"]["frames_per_clip"] == 100
