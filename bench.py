@@ -25,6 +25,7 @@ Besides the headline the same JSON line carries sub-records (each timed like `va
                        of the projector gradients (its own CUDA-event time and bus bandwidth)
   sweep              : BASELINE configs[3], 1024 synthetic clips sharded by clip index over the N ranks, micro-batch 16
   sweep_dedup        : the same sweep on EPIC-shaped clips (10 distinct frames tiled x10) through the de-duplicating path
+  default_switches   : the headline workload with every drop-in switch at its default (splice length readback on)
 Timing hygiene: W >= 3 warm-up steps; the per-step working set (582 MB of weights + ~0.5 GB of activations per
 clip) is several times the 126 MB L2, so no explicit L2 flush is needed between iterations.
 """
@@ -322,14 +323,15 @@ def setup(args):
     return c
 
 
-def get_host(c, D, dedup=0):
+def get_host(c, D, dedup=0, static_splice=True):
     """dedup = k > 0: config.hvlm_dedup_frames = k (static capacity: at most k distinct frames per clip, no host sync)."""
-    if (D, dedup) not in c.hosts:
-        h = build_host(D, c.dev, c.tower)
+    key = (D, dedup, static_splice)
+    if key not in c.hosts:
+        h = build_host(D, c.dev, c.tower, static_splice=static_splice)
         if dedup:
             h.config.hvlm_dedup_frames = dedup
-        c.hosts[(D, dedup)] = h
-    return c.hosts[(D, dedup)]
+        c.hosts[key] = h
+    return c.hosts[key]
 
 
 def make_step(host, hidden_dev):
@@ -417,10 +419,10 @@ def e2e_run(c, step, px_host, host_in, out_host, steps, transform=None):
 # ------------------------------------------------------------------------------------------------
 # headline: BASELINE configs[1] (or --hidden / --clips variants), forward
 # ------------------------------------------------------------------------------------------------
-def run_forward(c, args, D, B, steps, warmup, full=True):
+def run_forward(c, args, D, B, steps, warmup, full=True, static_splice=True):
     from hvlm_b200 import arch, ops
     dev, rank, world = c.dev, c.rank, c.world
-    host = get_host(c, D)
+    host = get_host(c, D, static_splice=static_splice)
     host.B = B
     ids, mask, labels, fh, fv = make_prompt(B, seed=rank)
     g = torch.Generator(device="cpu")
@@ -451,8 +453,9 @@ def run_forward(c, args, D, B, steps, warmup, full=True):
            "data": "synthetic (random-init ViT-L/14 + projector + embedding table, randn pixels)",
            "config": {"workload": workload_name(D, B), "clips_per_gpu": B, "frames_per_clip": FRAMES, "hidden": D,
                       "parallelism": f"clip-sharded dp{world}",
-                      "switches": "hvlm_static_splice=True (non-default: collator contract instead of a length readback; "
-                                  "violations raise from arch.check_deferred_status after the timed region)",
+                      "switches": ("hvlm_static_splice=True (non-default: collator contract instead of a length readback; "
+                                   "violations raise from arch.check_deferred_status after the timed region)")
+                      if static_splice else "all drop-in switches at their defaults",
                       "l2": "per-step working set (>1 GB) exceeds the 126 MB L2; no explicit flush"},
            "gpu_launches": int(launches),
            # model FLOPs of the reference computation (23 full layers) per second: what the path delivers, not what the
@@ -794,12 +797,19 @@ def run_ours(args):
                     res["gpu_eager_baseline"] = gpu_eager_baseline(c, args.hidden)
                 except Exception as e:      # a baseline leg must never take the headline down
                     res["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
+            # the same headline workload with every drop-in switch at its DEFAULT (one 4-byte-per-sample readback in the
+            # splice: the host cannot run ahead of the GPU across that point)
+            rdef = run_forward(c, args, args.hidden, args.clips, sub_steps, 3, full=False, static_splice=False)
             r3 = run_config3(c, args, sub_steps, 3)
             rt = run_train(c, args, args.hidden, 4, sub_steps, 3)
             rs = run_sweep(c, args, args.sweep_clips, 16)
             rd = run_sweep(c, args, args.sweep_clips, 16, tiled=10)
             if c.rank == 0:
                 res["config3"], res["train"], res["sweep"], res["sweep_dedup"] = r3, rt, rs, rd
+                res["default_switches"] = {"value": rdef["value"], "unit": "frames/s", "ms_per_step": rdef["ms_per_step"],
+                                           "steps": rdef["steps"], "what": "configs[1] with hvlm_static_splice off (the drop-in's "
+                                           "default): the splice reads the per-sample image-token counts back, like the "
+                                           "reference's own host syncs, and the launches of the next step are exposed"}
     elif mode == "train":
         res = run_train(c, args, args.hidden, 4 if args.clips == 1 else args.clips, args.steps, warm)
     elif mode == "config3":
