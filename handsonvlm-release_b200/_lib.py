@@ -66,6 +66,7 @@ SIGNATURES = {
     "hvlm_pool_slowfast_fwd_mapped": (i32, [p, i32, i64, p, p, i32, i32, i32, i32, i32, p]),
     "hvlm_pool_slowfast_bwd": (i32, [p, i32, p, i32, i32, i32, i32, i32, p]),
     "hvlm_splice_count": (i32, [p, i32, i32, p, p]),
+    "hvlm_splice_info": (i32, [p, i32, i32, i32, p, p]),
     "hvlm_splice_plan": (i32, [p, p, i32, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
     "hvlm_splice_plan_ragged": (i32, [p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p, p, p, p]),
     "hvlm_splice_fwd": (i32, [p, p, p, p, p, p, p, p, p, p, p, i32, i32, i32, i32, i32, i32, i32, i32, p, p, p, p]),

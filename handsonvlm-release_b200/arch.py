@@ -325,6 +325,37 @@ class VisualToTokenHelper:
 # ------------------------------------------------------------------------------------------------
 # splice
 # ------------------------------------------------------------------------------------------------
+class SplicePre:
+    """Image-token census of a batch of ids, taken EARLY: ``hvlm_splice_info`` + an asynchronous copy to pinned host memory
+    are enqueued at the top of ``prepare_inputs_labels_for_multimodal``, before the visual pipeline of the same call.  By the
+    time the splice needs the numbers (output length, error checks) the host has enqueued ~170 launches behind them, so
+    ``get()`` finds the copy complete and does not stall -- the reference's per-sample host syncs without draining the GPU."""
+
+    RING = 4
+
+    def __init__(self, host, input_ids: torch.Tensor, vocab: int):
+        B = input_ids.shape[0]
+        self.ids = input_ids
+        self.info = ops.splice_info(input_ids, vocab)                 # device int32 [4, B]
+        pool = host.__dict__.setdefault("_hvlm_pre_pool", {})
+        ring = pool.setdefault(B, [[], 0])
+        if len(ring[0]) < self.RING:
+            ring[0].append(torch.empty(4, B, dtype=torch.int32).pin_memory())
+        self.host = ring[0][ring[1] % len(ring[0])]
+        ring[1] += 1
+        self.host.copy_(self.info, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self._lists = None
+
+    def get(self):
+        """-> (counts, last image position, <hand_traj> tokens after it, bad-id flag), python lists per sample."""
+        if self._lists is None:
+            self.event.synchronize()
+            self._lists = tuple(self.host.tolist())
+        return self._lists
+
+
 def _raise_on_status(bits: int, static: bool = False):
     if static and bits & (L.PLAN_NOT_UNIFORM | L.PLAN_ERR_LEN_OVERFLOW):
         raise RuntimeError("hvlm_static_splice contract violated: every sample must carry exactly one image token "
@@ -341,7 +372,8 @@ def _raise_on_status(bits: int, static: bool = False):
 
 
 def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual, visual_mask=None,
-                  future_hands=None, is_evaluate: bool = False, im_start_end: bool = False, last_visual_end=None):
+                  future_hands=None, is_evaluate: bool = False, im_start_end: bool = False, last_visual_end=None,
+                  pre: Optional[SplicePre] = None):
     """Core of both prepare_inputs_labels_for_multimodal variants -> (attention_mask', embeds, labels').
     ``im_start_end``: the ``tune_mm_mlp_adapter and mm_use_im_start_end`` branch of llava_arch.py:146-161,172-181."""
     table = host.get_model().embed_tokens.weight
@@ -363,22 +395,6 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
     if visual.dtype != table.dtype:
         visual = visual.to(table.dtype)
     static = bool(getattr(host.config, "hvlm_static_splice", False)) and sizes is None
-    if static:
-        _deferred(host, input_ids.device).poll()                      # a broken contract of an EARLIER call raises here
-    counts = ops.splice_count(input_ids)
-    if static:
-        # collator contract (hybrid_dataset.py:155-158): exactly one image token per sample, equal T
-        Lout, uniform = T - 1 + Nv, True
-    else:
-        ks = counts.tolist()                                         # the ONE host sync of the general path
-        if sizes is None:
-            lens = [T + k * (Nv - 1) for k in ks]
-        else:
-            lens, slot = [], 0
-            for k in ks:                                             # a sample without image token still uses a slot
-                lens.append(T - k + sum(sizes[slot:slot + k]))
-                slot += max(k, 1)
-        Lout, uniform = max(lens), all(n == lens[0] for n in lens)
     hand_mode, n_hand = 0, 0
     if variant == L.SPLICE_HANDSONVLM:
         if not is_evaluate:
@@ -388,13 +404,41 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
             hand_mode, n_hand = 1, 4
         elif future_hands is not None:
             hand_mode, n_hand = 2, int(future_hands.shape[2])
+    if static:
+        # collator contract (hybrid_dataset.py:155-158): exactly one image token per sample, equal T.  No host sync at all;
+        # a broken contract of an EARLIER call raises here, this call's status is looked at by the next poll
+        _deferred(host, input_ids.device).poll()
+        counts = ops.splice_count(input_ids)
+        Lout, uniform = T - 1 + Nv, True
+    else:
+        # the census was taken before the visual pipeline was enqueued (prepare_inputs_labels_for_multimodal); a direct
+        # call takes it now.  Everything the reference would raise is raised HERE, from host numbers, before the plan
+        if pre is None or pre.ids is not input_ids:
+            pre = SplicePre(host, input_ids, table.shape[0])
+        ks, last_pos, hand_tail, bad = pre.get()
+        counts = pre.info[0]
+        if any(bad):
+            raise IndexError("index out of range in self")             # nn.Embedding's error for a bad token id
+        slot = 0
+        for k in ks:                                                   # cur_image_idx bookkeeping
+            if k > 0 and slot + k > n_img:
+                raise IndexError("index out of bounds: more image tokens than image features")
+            slot += max(k, 1)
+        if hand_mode:
+            for k, lp, nh in zip(ks, last_pos, hand_tail):
+                if k > 0 and ((hand_mode == 1 and nh > 4) or (hand_mode == 2 and lp + 1 < T and nh != n_hand)):
+                    raise AssertionError("number of <hand_traj> tokens does not match future_hands")
+        if sizes is None:
+            lens = [T + k * (Nv - 1) for k in ks]
+        else:
+            lens, slot = [], 0
+            for k in ks:                                             # a sample without image token still uses a slot
+                lens.append(T - k + sum(sizes[slot:slot + k]))
+                slot += max(k, 1)
+        Lout, uniform = max(lens), all(n == lens[0] for n in lens)
     src_index, hand_code, lens_d, hand_scale, status = ops.splice_plan(
         input_ids, counts, Nv, n_img, Lout, table.shape[0], variant, hand_mode, n_hand, slot_offsets, last_visual_end)
-    if not static:
-        _raise_on_status(int(status.item()))
-    else:
-        # no host sync here: the status word is copied to pinned memory behind the plan kernel and looked at by the next
-        # static call's poll() or by check_deferred_status(host)
+    if static:
         host._hvlm_splice_status = status
         _deferred(host, input_ids.device).add(status, lambda bits: _raise_on_status(bits, static=True))
     embeds, new_labels, new_mask = ops.splice_gather(
@@ -412,6 +456,13 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
     elif attention_mask.dtype != torch.bool:
         new_mask = new_mask.to(attention_mask.dtype)
     return new_mask, embeds, new_labels
+
+
+def _early_census(host, input_ids):
+    """The splice's image-token census, launched before the visual pipeline (None in static mode: no readback at all)."""
+    if bool(getattr(host.config, "hvlm_static_splice", False)) or not input_ids.is_cuda:
+        return None
+    return SplicePre(host, input_ids, host.get_model().embed_tokens.weight.shape[0])
 
 
 class LlavaMetaForCausalLM(ABC):
@@ -460,13 +511,14 @@ class LlavaMetaForCausalLM(ABC):
                                             dtype=attention_mask.dtype, device=attention_mask.device)
             return input_ids, attention_mask, past_key_values, None, labels
         ise = bool(getattr(self.config, "tune_mm_mlp_adapter", False) and getattr(self.config, "mm_use_im_start_end", False))
+        pre = _early_census(self, input_ids)
         image_features = self.visual_to_tokens(images)
         if isinstance(image_features, (list, tuple)):
             if all(x.shape == image_features[0].shape for x in image_features):
                 image_features = torch.stack(list(image_features), 0)
             # else: token blocks of different lengths go to the splice as a list (ragged plan)
         new_mask, embeds, new_labels = splice_tokens(self, L.SPLICE_LLAVA, input_ids, attention_mask, labels,
-                                                     image_features, im_start_end=ise)
+                                                     image_features, im_start_end=ise, pre=pre)
         return None, new_mask, past_key_values, embeds, new_labels
 
 
@@ -515,6 +567,7 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
             return self.videos_to_tokens(images)
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images, **kwargs):
+        pre = _early_census(self, input_ids)
         helper = VisualToTokenHelper(images_raw_encode=self.get_model().get_vision_tower(),
                                      images_mm_projector=self.get_model().mm_projector,
                                      fuse_input_mode=self.config.fuse_input_mode,
@@ -528,7 +581,7 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
             # slot takes the image position's label and mask entry, last_visual_token_index is left untouched
             new_mask, embeds, new_labels = splice_tokens(
                 self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None, None, True,
-                im_start_end=True)
+                im_start_end=True, pre=pre)
             return None, new_mask, past_key_values, embeds, new_labels
         # side effect of the reference (handsonvlm.py:288): a 0-d int64 tensor, written by the plan kernel for the last
         # image token of the last sample that has one (left at its previous value when no sample has an image token)
@@ -538,7 +591,7 @@ class HandsOnVLMMetaForCausalLM(LitaMetaForCausalLM):
             lve = torch.full((), -1, dtype=torch.int64, device=input_ids.device)
         new_mask, embeds, new_labels = splice_tokens(
             self, L.SPLICE_HANDSONVLM, input_ids, attention_mask, labels, visual_tokens, None,
-            kwargs.get("future_hands"), kwargs.get("is_evaluate", False), last_visual_end=lve)
+            kwargs.get("future_hands"), kwargs.get("is_evaluate", False), last_visual_end=lve, pre=pre)
         self.__dict__["last_visual_token_index"] = lve
         return None, new_mask, past_key_values, embeds, new_labels
 

@@ -32,6 +32,55 @@ __global__ void splice_count_kernel(const int64_t* __restrict__ ids, int T, int3
     }
 }
 
+// Everything the HOST needs to size the output and to raise the reference's errors, from the ids alone -- so it can be
+// launched (and copied out asynchronously) BEFORE the visual pipeline of the same call and read without stalling once that
+// pipeline has been enqueued.  info is [4][B]: image-token count | position of the last image token (-1: none) | number of
+// <hand_traj> tokens after it | 1 if some id is outside [0, vocab) and not the image token.
+__global__ void __launch_bounds__(kPlanThreads)
+splice_info_kernel(const int64_t* __restrict__ ids, int B, int T, int vocab, int32_t* __restrict__ info) {
+    __shared__ int s_cnt, s_last, s_bad, s_hand;
+    const int b = blockIdx.x;
+    const int64_t* row = ids + static_cast<int64_t>(b) * T;
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_last = -1;
+        s_bad = 0;
+        s_hand = 0;
+    }
+    __syncthreads();
+    int cnt = 0, last = -1, bad = 0;
+    for (int p = threadIdx.x; p < T; p += blockDim.x) {
+        const int64_t tok = row[p];
+        if (tok == HVLM_IMAGE_TOKEN_INDEX) {
+            ++cnt;
+            last = p;
+        } else if (tok < 0 || tok >= vocab) {
+            bad = 1;
+        }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    last = __reduce_max_sync(0xffffffffu, last);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt, cnt);
+        atomicMax(&s_last, last);
+        atomicOr(&s_bad, bad);
+    }
+    __syncthreads();
+    const int last_pos = s_last;
+    int hand = 0;
+    for (int p = last_pos + 1 + threadIdx.x; p < T; p += blockDim.x) hand += (row[p] == HVLM_HAND_TRAJ_TOKEN_ID);
+    hand = __reduce_add_sync(0xffffffffu, hand);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_hand, hand);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info[b] = s_cnt;
+        info[B + b] = last_pos;
+        info[2 * B + b] = s_hand;
+        info[3 * B + b] = s_bad;
+    }
+}
+
 __global__ void __launch_bounds__(kPlanThreads)
 splice_plan_kernel(const int64_t* __restrict__ ids, const int32_t* __restrict__ counts,
                    const int32_t* __restrict__ slot_offsets /* NULL: every slot has Nv rows */, int B, int T, int Nv,
@@ -279,6 +328,14 @@ extern "C" int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* coun
     StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
     splice_count_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(ids, T, counts);
     return check_last("splice_count");
+}
+
+extern "C" int hvlm_splice_info(const int64_t* ids, int B, int T, int vocab, int32_t* info, void* stream) {
+    using namespace hvlm;
+    if (!ids || !info || B <= 0 || T <= 0 || vocab <= 0) return HVLM_ERR_BAD_ARG;
+    StageTimer st(HVLM_STAGE_SPLICE, static_cast<cudaStream_t>(stream));
+    splice_info_kernel<<<B, kPlanThreads, 0, static_cast<cudaStream_t>(stream)>>>(ids, B, T, vocab, info);
+    return check_last("splice_info");
 }
 
 static int splice_plan_impl(const int64_t* ids, const int32_t* counts, const int32_t* slot_offsets, int B, int T, int Nv,

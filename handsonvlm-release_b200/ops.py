@@ -437,6 +437,17 @@ def splice_count(ids: torch.Tensor) -> torch.Tensor:
     return counts
 
 
+def splice_info(ids: torch.Tensor, vocab: int) -> torch.Tensor:
+    """-> int32 [4, B]: image-token count | last image-token position | <hand_traj> tokens after it | bad-id flag."""
+    _need_cuda(ids)
+    ensure_device()
+    ids = ids.contiguous()
+    B, T = ids.shape
+    info = torch.empty(4, B, dtype=torch.int32, device=ids.device)
+    L.check(L.lib().hvlm_splice_info(_p(ids), B, T, int(vocab), _p(info), _stream()), "hvlm_splice_info")
+    return info
+
+
 def splice_plan(ids: torch.Tensor, counts: torch.Tensor, Nv: int, n_img: int, Lout: int, vocab: int, variant: int,
                 hand_mode: int, n_hand: int, slot_offsets: Optional[torch.Tensor] = None,
                 last_visual_end: Optional[torch.Tensor] = None):

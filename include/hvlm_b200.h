@@ -227,6 +227,12 @@ HVLM_API int hvlm_pool_slowfast_bwd(const void* dout, int dout_dtype, void* dtok
 #define HVLM_PLAN_NOT_UNIFORM 16        /* lens differ between samples (ragged output)            */
 
 HVLM_API int hvlm_splice_count(const int64_t* ids, int B, int T, int32_t* counts, void* stream);
+/* Step 1 with everything the HOST side needs to size the output and to raise the reference's errors, from the ids alone:
+ * info int32 [4][B] = image-token count (usable as `counts` of hvlm_splice_plan) | position of the last image token (-1:
+ * none) | number of <hand_traj> tokens after it | 1 if some id is outside [0, vocab) and is not the image token.
+ * Launched before the visual pipeline of the same call and copied out asynchronously, it is on the host long before the
+ * splice needs it: the reference's per-sample host syncs (llava_arch.py:127,137; handsonvlm.py:234,247) without a stall. */
+HVLM_API int hvlm_splice_info(const int64_t* ids, int B, int T, int vocab, int32_t* info, void* stream);
 HVLM_API int hvlm_splice_plan(const int64_t* ids, const int32_t* counts /*from hvlm_splice_count*/, int B, int T, int Nv,
                      int n_img, int L, int vocab, int variant,
                      int hand_mode /*0 none, 1 training (4 points, cnt/4 scaling), 2 eval (n points)*/,
