@@ -25,6 +25,8 @@
 //     every global store instruction writes four full 128-byte lines.
 //   * next item's Q/K (V) loads are issued as soon as the current item's last S (PV) MMA has retired and the
 //     CUDA-core readers of that buffer have signalled.
+#include <cstdlib>
+
 #include "hvlm_internal.cuh"
 #include "hvlm_ptx.cuh"
 
@@ -47,6 +49,14 @@ constexpr int kOffPart = kOffPT + 2 * 272 * 4; // float[4][64]: per-warp partial
 constexpr int kOffBar = kOffPart + 4 * 64 * 4;
 constexpr int kSmem = kOffBar + 128 + 1024;    // + barriers + alignment slack
 static_assert(2 * (kSmem + 1024) <= 228 * 1024, "two CTAs must fit in one SM's shared memory");
+// ping-pong variant: ONE CTA per SM runs two copies ("programs") of the algorithm, each with its own shared-memory image
+// and its own 256 TMEM columns; named barriers make their exp passes take turns on the MUFU pipe
+constexpr int kSmemHalf = ((kOffBar + 128 + 1023) / 1024) * 1024;
+constexpr int kSmemPP = 2 * kSmemHalf + 1024;
+static_assert(kSmemPP <= 227 * 1024, "both programs must fit in one CTA's shared memory");
+constexpr int kBarTurnA = 5;                   // program B arrives, program A waits: "B's exp pass is over"
+constexpr int kBarTurnB = 6;                   // program A arrives, program B waits
+constexpr bool kPingPongDefault = false;
 constexpr uint32_t kQKTx = 4 * kTile + 2 * kTailTile;
 constexpr uint32_t kVTx = 2 * kTile + 128;
 constexpr int kPCol = 0;                   // P (bf16 pairs) : TMEM columns [0,128)
@@ -125,16 +135,32 @@ __device__ __forceinline__ float exp_chunk32(const uint32_t (&v)[32], float log2
 #define ATTN_TRACE(role, slot)                                                                          \
     do {                                                                                                \
         if (trace != nullptr && it < 4)                                                                 \
-            trace[((static_cast<size_t>(blockIdx.x) * 5 + (role)) * 4 + it) * 16 + (slot)] = clock64();   \
+            trace[((static_cast<size_t>(vcta) * 5 + (role)) * 4 + it) * 16 + (slot)] = clock64();   \
     } while (0)
 
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// PP = false: 160 threads, two CTAs per SM (the co-resident CTA's MMAs overlap this one's softmax).
+// PP = true : 320 threads, one CTA per SM = two programs A / B (threads 0..159 / 160..319) that walk interleaved item
+//             lists; their exp passes strictly alternate (A, B, A, B ...), so a program's MUFU-bound pass never shares the
+//             pipe with the other's and always overlaps the other's TMEM / epilogue / MMA-wait phases.
+template <bool PP>
+__global__ void __launch_bounds__(PP ? 2 * kThreads : kThreads, PP ? 1 : 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail16,
                     const __grid_constant__ CUtensorMap tm_tail1, __nv_bfloat16* __restrict__ out, int n_items,
-                    long long* __restrict__ trace) {
+                    long long* __restrict__ trace, int take_turns) {
     extern __shared__ uint8_t smem_raw[];
+    const int half = PP ? static_cast<int>(threadIdx.x) / kThreads : 0;      // program of this thread
+    const int tid = static_cast<int>(threadIdx.x) - half * kThreads;
+    // program B of CTA b walks the item list of "virtual CTA" b + gridDim: per SM the two lists then differ by at most one
+    // item in total, exactly like CTAs b and b + 148 of the two-CTA kernel (2b / 2b + 1 would pair the long lists)
+    const int vcta = static_cast<int>(blockIdx.x) + (PP ? half * static_cast<int>(gridDim.x) : 0);
+    const int vgrid = PP ? static_cast<int>(gridDim.x) * 2 : static_cast<int>(gridDim.x);
     const uint32_t raw = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem0 = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* smem = smem0 + half * kSmemHalf;
     uint8_t* sQ = smem + kOffQ;
     uint8_t* sK = smem + kOffK;
     uint8_t* sV = smem + kOffV;
@@ -156,10 +182,12 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     uint64_t* t_full = bars + 6;     // MMA  -> softmax         (once per item): token-256 score blocks written
     uint64_t* t_read = bars + 7;     // softmax(128) -> MMA     (once, first item only): those blocks were read
     uint64_t* vt_read = bars + 8;    // softmax(128) -> MMA     (once per item): V / v row 256 consumed by the CUDA cores
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem0 + kOffBar + 9 * 8);   // program A's slot serves both
+    constexpr int kCols = PP ? 512 : 256;
 
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int bar_sc = 1 + 2 * half, bar_part = 2 + 2 * half;     // per-program named barriers
 
     if (warp == 0) {
         if (lane == 0) {
@@ -178,12 +206,12 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<256>(tmem_slot);
+        if (half == 0) tmem_alloc<kCols>(tmem_slot);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot + static_cast<uint32_t>(half * 256);
     pdl_launch_dependents();
     pdl_wait();              // everything above overlapped the previous kernel's tail
 
@@ -254,9 +282,9 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         int it = 0;
         uint32_t n2 = 0;   // running tile counter (s_full / p_full / o_full / o_read complete once per tile)
         // items are walked last-to-first: the QKV GEMM wrote the last frames last, so they are still in L2
-        if (static_cast<int>(blockIdx.x) < n_items) {
-            load_qk(n_items - 1 - blockIdx.x);
-            load_v(n_items - 1 - blockIdx.x);
+        if (vcta < n_items) {
+            load_qk(n_items - 1 - vcta);
+            load_v(n_items - 1 - vcta);
             mbar_wait(qk_full, 0);
             tc_fence_after();
             issue_tail();
@@ -264,8 +292,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             tc_fence_after();
             issue_s(0);
         }
-        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++it) {
-            const int next_idx = idx + gridDim.x;
+        for (int idx = vcta; idx < n_items; idx += vgrid, ++it) {
+            const int next_idx = idx + vgrid;
             const int next = n_items - 1 - next_idx;
             if (lane == 0) ATTN_TRACE(0, 0);
             for (int tile = 0; tile < 2; ++tile, ++n2) {
@@ -317,7 +345,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         }
     } else {
         // ===================== softmax + epilogue warps: one query row per thread =====================
-        const int q = warp & 3;                       // TMEM lane quarter
+        const int q = (static_cast<int>(threadIdx.x) >> 5) & 3;   // TMEM lane quarter: fixed by the HARDWARE warp index
         const int r = q * 32 + lane;                  // row inside the 128-row tile
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         uint8_t* stage = sStage + (warp - 1) * 1024;  // this warp's 8-row x 128-byte transpose buffer
@@ -325,7 +353,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         uint32_t n2 = 0;
         int it = 0;
         uint32_t tl[4] = {0u, 0u, 0u, 0u};             // token-256 scores of the upcoming item (see kTCol)
-        if (static_cast<int>(blockIdx.x) < n_items) {
+        if (vcta < n_items) {
             mbar_wait(t_full, 0);
             tc_fence_after();
 #pragma unroll
@@ -334,10 +362,10 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             tc_fence_before();
             mbar_arrive(t_read);
         }
-        for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++it) {
+        for (int idx = vcta; idx < n_items; idx += vgrid, ++it) {
             const int item = n_items - 1 - idx;
             const int f = item >> 4, head = item & 15;
-            const bool has_next = idx + static_cast<int>(gridDim.x) < n_items;
+            const bool has_next = idx + vgrid < n_items;
             const bool tr = (lane == 0);
             if (tr) ATTN_TRACE(warp, 0);
             const float s_tail[2] = {__uint_as_float(tl[0]), __uint_as_float(tl[1])};
@@ -384,6 +412,14 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 //      16 P columns land in S columns that were already consumed)
                 const float mxl = mx * kLog2e;
                 float sum = 0.f, sum1 = 0.f;
+                if (PP && take_turns) {
+                    // wait for the other program's exp pass to end (A goes first: nothing to wait for on its first tile)
+                    if (half == 0) {
+                        if (n2 > 0) named_bar_sync(kBarTurnA, 256);
+                    } else {
+                        named_bar_sync(kBarTurnB, 256);
+                    }
+                }
                 {
                     uint32_t va[32], vb[32], pk[16];
                     tmem_ld32(t_lane, va);
@@ -399,6 +435,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         tmem_st16(t_lane + kPCol + (c + 1) * 16, pk);
                     }
                 }
+                if (PP && take_turns) named_bar_arrive(half == 0 ? kBarTurnB : kBarTurnA, 256);   // the MUFU pipe is the other's
                 const float p_tail = fast_exp2(fmaf(s_tail[tile], kLog2e, -mxl));
                 sum += sum1 + p_tail;
                 const float inv_sum = 1.0f / sum;
@@ -410,7 +447,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 // ---- the 257th query row on CUDA cores, in the shadow of the P*V MMAs
                 if (tile == 0) {
                     // softmax of its 257 scores (every warp redundantly) and P*V over this warp's 64 keys
-                    named_bar_sync(1, 128);            // all scores are in sSc
+                    named_bar_sync(bar_sc, 128);       // all scores are in sSc
                     mbar_wait(v_full, it & 1);         // V / v row 256 are read by the CUDA cores from here on
                     const float s256 = sSc[256];
                     float sc[8];
@@ -461,7 +498,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                         dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
                         dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                     }
-                    named_bar_sync(2, 128);            // the four partial sums are in sPart
+                    named_bar_sync(bar_part, 128);     // the four partial sums are in sPart
                     if (q == 1) {
                         const int d = 2 * lane;
                         const uint32_t va = *reinterpret_cast<const uint32_t*>(sVT + lane * 4);
@@ -532,11 +569,25 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             }
             mbar_arrive(vt_read);
         }
+        if (PP && take_turns) {
+            // program B may own one item less than A: it still takes its turns, so that A's waits are always answered
+            if (half == 1) {
+                const int va = vcta - static_cast<int>(gridDim.x);     // program A's list
+                const int items_a = (va < n_items) ? (n_items - va + vgrid - 1) / vgrid : 0;
+                for (int extra = it; extra < items_a; ++extra) {
+#pragma unroll 1
+                    for (int tile = 0; tile < 2; ++tile) {
+                        named_bar_sync(kBarTurnB, 256);
+                        named_bar_arrive(kBarTurnA, 256);
+                    }
+                }
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem_base);
+    if (warp == 0 && half == 0) tmem_dealloc<kCols>(*tmem_slot);
 }
 
 }  // namespace attn
@@ -559,18 +610,37 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
     if (rc) return rc;
     rc = make_qkv_hm_tmap(&tt1, qkv_hm, n_frames * kS, 1);
     if (rc) return rc;
+    // HVLM_ATTN_PINGPONG=0 / 1 selects the two-CTAs-per-SM kernel / the one-CTA ping-pong kernel (default: see DESIGN.md)
+    static const bool pingpong = []() {
+        const char* e = getenv("HVLM_ATTN_PINGPONG");
+        return e ? e[0] == '1' : kPingPongDefault;
+    }();
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(attn_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess ||
+            cudaFuncSetAttribute(attn_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPP) != cudaSuccess)
             return HVLM_ERR_CUDA;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const int max_ctas = 2 * num_sms();
-    const int grid = n_items < max_ctas ? n_items : max_ctas;
-    if (launch_pdl_cls(2, attn_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1, static_cast<__nv_bfloat16*>(out), n_items,
-                   trace) != cudaSuccess) {
+    static const int take_turns = []() {
+        const char* e = getenv("HVLM_ATTN_PP_TURNS");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    cudaError_t err;
+    if (pingpong) {
+        const int want = (n_items + 1) / 2;
+        const int grid = want < num_sms() ? want : num_sms();
+        err = launch_pdl_cls(2, attn_tcgen05_kernel<true>, dim3(grid), dim3(2 * kThreads), kSmemPP, s, tq, tt16, tt1,
+                             static_cast<__nv_bfloat16*>(out), n_items, trace, take_turns);
+    } else {
+        const int max_ctas = 2 * num_sms();
+        const int grid = n_items < max_ctas ? n_items : max_ctas;
+        err = launch_pdl_cls(2, attn_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1,
+                             static_cast<__nv_bfloat16*>(out), n_items, trace, 0);
+    }
+    if (err != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
     }

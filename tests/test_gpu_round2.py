@@ -589,19 +589,35 @@ bq = synth.gen("o.bq", (3072,), 0.1, 3).to(dev)
 qkv = ops.vit_qkv(y, wq, bq, 3)                                  # [48, M, 64] column-block-major
 ref = (y.float() @ wq.float().t() + bq).reshape(3 * 257, 48, 64).permute(1, 0, 2)
 assert relmax(qkv, ref) <= 5e-3
+# attention (HVLM_ATTN_PINGPONG=1: one CTA per SM, two programs taking turns on the exp pass), 37 frames = 592 items:
+# uneven item lists, program B's padding rounds
+F = 37
+qb = torch.randn(48, F * 257, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(3)).to(torch.bfloat16)
+qb[:16] *= 0.3
+out = ops.vit_attention(qb)
+t = qb.reshape(3, 16, F, 257, 64).float()
+ref = torch.nn.functional.scaled_dot_product_attention(t[0], t[1], t[2], scale=1.0)
+assert relmax(out.reshape(F, 257, 16, 64).permute(2, 0, 1, 3), ref) <= 8e-3
+assert torch.equal(out, ops.vit_attention(qb))
+for F2 in (1, 2, 19):
+    q2 = qb[:, : F2 * 257].contiguous()
+    t2 = q2.reshape(3, 16, F2, 257, 64).float()
+    r2_ = torch.nn.functional.scaled_dot_product_attention(t2[0], t2[1], t2[2], scale=1.0)
+    assert relmax(ops.vit_attention(q2).reshape(F2, 257, 16, 64).permute(2, 0, 1, 3), r2_) <= 8e-3, F2
 print("optin ok")
 '''
 
 
 def test_opt_in_kernel_variants_stay_correct(tmp_path):
-    """The experiment switches that are off by default (residual-load epilogue, second epilogue group for the QKV GEMM) are
-    read once per process, so they are exercised in a child process: same tolerances as the default kernels."""
+    """The experiment switches that are off by default (residual-load epilogue, second epilogue group for the QKV GEMM,
+    ping-pong attention) are read once per process, so they are exercised in a child process: same tolerances as the
+    default kernels."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "optin.py"
     script.write_text(_OPTIN_SCRIPT)
-    env = dict(os.environ, HVLM_RESID_LOAD_MAXK="4096", HVLM_QKV_EPI_GROUPS="2")
+    env = dict(os.environ, HVLM_RESID_LOAD_MAXK="4096", HVLM_QKV_EPI_GROUPS="2", HVLM_ATTN_PINGPONG="1")
     r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "optin ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
 
