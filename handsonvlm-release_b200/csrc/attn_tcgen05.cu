@@ -57,7 +57,6 @@ static_assert(kSmemPP <= 227 * 1024, "both programs must fit in one CTA's shared
 constexpr int kBarTurnA = 5;                   // program B arrives, program A waits: "B's exp pass is over"
 constexpr int kBarTurnB = 6;                   // program A arrives, program B waits
 constexpr bool kPingPongDefault = false;
-constexpr int kDephaseDefaultNs = 0;
 constexpr uint32_t kQKTx = 4 * kTile + 2 * kTailTile;
 constexpr uint32_t kVTx = 2 * kTile + 128;
 constexpr int kPCol = 0;                   // P (bf16 pairs) : TMEM columns [0,128)
@@ -151,7 +150,7 @@ template <bool PP>
 __global__ void __launch_bounds__(PP ? 2 * kThreads : kThreads, PP ? 1 : 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_tail16,
                     const __grid_constant__ CUtensorMap tm_tail1, __nv_bfloat16* __restrict__ out, int n_items,
-                    long long* __restrict__ trace, int take_turns, int dephase_ns) {
+                    long long* __restrict__ trace, int take_turns) {
     extern __shared__ uint8_t smem_raw[];
     const int half = PP ? static_cast<int>(threadIdx.x) / kThreads : 0;      // program of this thread
     const int tid = static_cast<int>(threadIdx.x) - half * kThreads;
@@ -282,14 +281,6 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 
         int it = 0;
         uint32_t n2 = 0;   // running tile counter (s_full / p_full / o_full / o_read complete once per tile)
-        // De-phasing (two-CTA kernel): the two CTAs of an SM start together and do identical work per tile, so their
-        // MUFU-bound exp passes would collide tile after tile.  The CTAs of the second wave (the second CTA of every SM)
-        // start a fraction of a tile period late; the offset persists because both run the same period.
-        if (!PP && dephase_ns != 0) {
-            // > 0: second wave = upper half of the grid (CTA b and b + #SMs share an SM); < 0: odd CTAs (A/B probe)
-            const bool late = dephase_ns > 0 ? (2 * blockIdx.x >= gridDim.x) : ((blockIdx.x & 1u) != 0);
-            if (late) __nanosleep(static_cast<unsigned>(dephase_ns > 0 ? dephase_ns : -dephase_ns));
-        }
         // items are walked last-to-first: the QKV GEMM wrote the last frames last, so they are still in L2
         if (vcta < n_items) {
             load_qk(n_items - 1 - vcta);
@@ -633,10 +624,6 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
             return HVLM_ERR_CUDA;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    static const int dephase_ns = []() {
-        const char* e = getenv("HVLM_ATTN_DEPHASE_NS");
-        return e ? atoi(e) : kDephaseDefaultNs;
-    }();
     static const int take_turns = []() {
         const char* e = getenv("HVLM_ATTN_PP_TURNS");
         return (e && e[0] == '0') ? 0 : 1;
@@ -646,12 +633,12 @@ static int launch_attention_impl(const void* qkv_hm, void* out, int n_frames, cu
         const int want = (n_items + 1) / 2;
         const int grid = want < num_sms() ? want : num_sms();
         err = launch_pdl_cls(2, attn_tcgen05_kernel<true>, dim3(grid), dim3(2 * kThreads), kSmemPP, s, tq, tt16, tt1,
-                             static_cast<__nv_bfloat16*>(out), n_items, trace, take_turns, 0);
+                             static_cast<__nv_bfloat16*>(out), n_items, trace, take_turns);
     } else {
         const int max_ctas = 2 * num_sms();
         const int grid = n_items < max_ctas ? n_items : max_ctas;
         err = launch_pdl_cls(2, attn_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmem, s, tq, tt16, tt1,
-                             static_cast<__nv_bfloat16*>(out), n_items, trace, 0, dephase_ns);
+                             static_cast<__nv_bfloat16*>(out), n_items, trace, 0);
     }
     if (err != cudaSuccess) {
         cudaGetLastError();
