@@ -15,7 +15,7 @@ def build(verbose: bool = False) -> str:
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `build()` works before torch is paged in
-    if name in ("ops", "tower", "arch", "weights", "dist", "traj_decoder", "builder"):
+    if name in ("ops", "tower", "arch", "weights", "dist", "traj_decoder", "builder", "integrate"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     if name in ("CLIPVisionTower",):
@@ -25,6 +25,9 @@ def __getattr__(name):
                 "gather_hand_traj_states"):
         from . import arch
         return getattr(arch, name)
+    if name in ("patch_reference", "unpatch_reference"):
+        from . import integrate
+        return getattr(integrate, name)
     if name == "build_vision_tower":
         from .builder import build_vision_tower
         return build_vision_tower

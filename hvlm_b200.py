@@ -1,11 +1,34 @@
 """Import alias: ``import hvlm_b200`` == the package in ``handsonvlm-release_b200/`` (whose directory name,
-fixed by the project layout, is not a valid Python identifier)."""
+fixed by the project layout, is not a valid Python identifier).  Submodules resolve to the SAME module objects under both
+names (``hvlm_b200.tower is sys.modules['handsonvlm-release_b200.tower']``): one copy of every class and registry."""
 import importlib
+import importlib.abc
+import importlib.machinery
 import os
 import sys
 
 _root = os.path.dirname(os.path.abspath(__file__))
 if _root not in sys.path:
     sys.path.insert(0, _root)
-_pkg = importlib.import_module("handsonvlm-release_b200")
+_REAL = "handsonvlm-release_b200"
+_pkg = importlib.import_module(_REAL)
+
+
+class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """``hvlm_b200.<sub>`` -> the already imported (or now imported) ``handsonvlm-release_b200.<sub>`` module."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.startswith(__name__ + "."):
+            return importlib.machinery.ModuleSpec(fullname, self)
+        return None
+
+    def create_module(self, spec):
+        return importlib.import_module(_REAL + spec.name[len(__name__):])
+
+    def exec_module(self, module):
+        pass
+
+
+if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):
+    sys.meta_path.insert(0, _AliasFinder())
 sys.modules[__name__] = _pkg

@@ -116,3 +116,47 @@ def test_reference_loader_and_trainer_walk(one_layer_sd):
         assert isinstance(model.mm_projector, torch.nn.Linear) and model.mm_projector.in_features == 1024
     finally:
         ref_arch.build_vision_tower = orig
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present (GPU box)")
+def test_patch_reference_swaps_the_hot_path_only(one_layer_sd):
+    """hvlm_b200.patch_reference(): the reference's own classes, imported unmodified, dispatch their hot-path methods to the
+    drop-ins afterwards (and nothing else changes); unpatch restores them.  A CPU call through the patched reference mixin
+    reaches our ops and fails loudly there (no CPU fallback) -- proof that the reference code path is no longer taken."""
+    from hvlm_b200 import arch, integrate
+    sd, path = one_layer_sd
+    ns = ref_shim.load()
+    if ns.handsonvlm is None:
+        pytest.skip("reference handsonvlm module does not import here")
+    ref_prep = ns.handsonvlm.HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal
+    ref_v2t = ns.lita_arch.LitaMetaForCausalLM.videos_to_tokens
+    ref_fwd = ns.handsonvlm.HandsOnVLMForCausalLM.forward
+    done = integrate.patch_reference()
+    try:
+        assert "llava.model.llava_arch.LlavaMetaForCausalLM.prepare_inputs_labels_for_multimodal" in done
+        assert "handsonvlm.model.language_model.handsonvlm.HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal" in done
+        H = ns.handsonvlm.HandsOnVLMForCausalLM
+        assert H.prepare_inputs_labels_for_multimodal is arch.HandsOnVLMMetaForCausalLM.prepare_inputs_labels_for_multimodal
+        assert ns.lita_arch.LitaMetaForCausalLM.videos_to_tokens is arch.LitaMetaForCausalLM.videos_to_tokens
+        assert ns.llava_arch.build_vision_tower is build_vision_tower
+        assert ns.clip_encoder.CLIPVisionTower is CLIPVisionTower and ns.v2t.VisualToTokenHelper is arch.VisualToTokenHelper
+        assert ns.handsonvlm.VisualToTokenHelper is arch.VisualToTokenHelper and hasattr(H, "gather_hand_traj_states")
+        assert H.forward is ref_fwd                                     # everything off the path is untouched
+        # a reference-side host that mixes in the (patched) reference mixin, like LitaLlamaForCausalLM does
+        tower = CLIPVisionTower(path, _args(path), delay_load=True)
+        tower.load_model()
+        proj = torch.nn.Linear(1024, 64)
+
+        class Host(ns.lita_arch.LitaMetaForCausalLM):
+            config = types.SimpleNamespace(input_type="video", video_arch="temporal_spatial_pool")
+
+            def get_model(self):
+                return types.SimpleNamespace(get_vision_tower=lambda: tower, mm_projector=proj, vision_tower=tower)
+
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Host().visual_to_tokens(torch.zeros(1, 2, 3, 224, 224))
+    finally:
+        integrate.unpatch_reference()
+    assert ns.handsonvlm.HandsOnVLMForCausalLM.prepare_inputs_labels_for_multimodal is ref_prep
+    assert ns.lita_arch.LitaMetaForCausalLM.videos_to_tokens is ref_v2t
+    assert not hasattr(ns.handsonvlm.HandsOnVLMForCausalLM, "gather_hand_traj_states")
