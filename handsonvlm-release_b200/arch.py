@@ -335,7 +335,7 @@ class SplicePre:
 
     def __init__(self, host, input_ids: torch.Tensor, vocab: int):
         B = input_ids.shape[0]
-        self.ids = input_ids
+        self.ids, self.version = input_ids, input_ids._version        # the census is only valid for THIS content
         self.info = ops.splice_info(input_ids, vocab)                 # device int32 [4, B]
         pool = host.__dict__.setdefault("_hvlm_pre_pool", {})
         ring = pool.setdefault(B, [[], 0])
@@ -413,7 +413,7 @@ def splice_tokens(host, variant: int, input_ids, attention_mask, labels, visual,
     else:
         # the census was taken before the visual pipeline was enqueued (prepare_inputs_labels_for_multimodal); a direct
         # call takes it now.  Everything the reference would raise is raised HERE, from host numbers, before the plan
-        if pre is None or pre.ids is not input_ids:
+        if pre is None or pre.ids is not input_ids or pre.version != input_ids._version:
             pre = SplicePre(host, input_ids, table.shape[0])
         ks, last_pos, hand_tail, bad = pre.get()
         counts = pre.info[0]

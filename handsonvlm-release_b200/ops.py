@@ -119,8 +119,14 @@ _wgrad_sinks: dict = {}
 
 
 def register_wgrad_sink(weight_shape, device, dW: torch.Tensor, db: Optional[torch.Tensor]) -> None:
+    """One sink per (projector weight shape, device): the backward of ``hvlm::linear`` finds it by that key (the weight it
+    sees may be a bf16 copy of an fp32 parameter, so there is no stabler identity).  Two projectors of the same shape on
+    one device cannot both own a sink -- the second registration raises; use ``ProjectorGradReducer(use_sink=False)``."""
     assert dW.dtype == torch.float32 and tuple(dW.shape) == tuple(weight_shape) and dW.is_contiguous()
-    _wgrad_sinks[(tuple(weight_shape), torch.device(device))] = (dW, db)
+    key = (tuple(weight_shape), torch.device(device))
+    if key in _wgrad_sinks and _wgrad_sinks[key][0].data_ptr() != dW.data_ptr():
+        raise RuntimeError(f"a gradient bucket is already registered for projector weights of shape {key[0]} on {key[1]}")
+    _wgrad_sinks[key] = (dW, db)
 
 
 def unregister_wgrad_sink(weight_shape, device) -> None:
