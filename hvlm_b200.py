@@ -23,10 +23,19 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         return None
 
     def create_module(self, spec):
-        return importlib.import_module(_REAL + spec.name[len(__name__):])
+        real = importlib.import_module(_REAL + spec.name[len(__name__):])
+        self._specs[spec.name] = real.__spec__
+        return real
 
     def exec_module(self, module):
-        pass
+        # the import machinery has just pointed module.__spec__ at the alias spec; the module keeps its real one (its
+        # relative imports resolve against __package__ / __spec__.parent == the real package)
+        for name, real_spec in list(self._specs.items()):
+            if sys.modules.get(real_spec.name) is module:
+                module.__spec__ = real_spec
+                del self._specs[name]
+
+    _specs: dict = {}
 
 
 if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):
