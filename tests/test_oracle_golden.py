@@ -367,3 +367,51 @@ def test_preprocess_matches_reference_fixture(golden, name):
     assert tuple(padded.shape[1:3][::-1]) == tuple(int(v) for v in g["padded_size"])
     pd = restate.clip_normalize_u8(restate.clip_resize_center_crop_u8(padded))[0]
     assert float((pd[:, ::2, ::2] - T(g["pad"])).abs().max()) <= 1e-6
+
+
+def test_resample_restatement_vs_pil_random_sizes():
+    """Seeded sweep over (in, out) size pairs -- strong down-scaling, up-scaling, identity, tiny images -- of the oracle's
+    Pillow restatement against PIL.Image.resize(BICUBIC) itself, both passes, bit-exact."""
+    from PIL import Image
+    rng = np.random.RandomState(2024)
+    for case in range(40):
+        H, W = int(rng.randint(3, 260)), int(rng.randint(3, 260))
+        nh, nw = int(rng.randint(2, 260)), int(rng.randint(2, 260))
+        img = rng.randint(0, 256, (H, W, 3), dtype=np.uint8)
+        xb, xc = restate.resample_table(W, nw)
+        yb, yc = restate.resample_table(H, nh)
+        tmp = restate._resample_axis_last(np.ascontiguousarray(img.transpose(0, 2, 1)), xb, xc)       # [H,3,nw]
+        out = restate._resample_axis_last(np.ascontiguousarray(tmp.transpose(1, 2, 0)), yb, yc)      # [3,nw,nh]
+        out = out.transpose(2, 1, 0)
+        ref = np.asarray(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+        assert np.array_equal(out, ref), (case, H, W, nh, nw)
+
+
+def test_resize_plan_host_matches_restatement_for_random_geometries():
+    """hvlm_resize_plan_host / hvlm_resize_tables_host (host side of the C ABI): geometry as transformers derives it,
+    tables == the oracle's sliced to the crop window, spans (x_lo, x_cols, rows_cap) consistent with those tables."""
+    import ctypes as C
+    import hvlm_b200
+    from hvlm_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.RandomState(7)
+    for case in range(25):
+        H, W = int(rng.randint(224, 1300)), int(rng.randint(224, 2000))
+        plan = L.ResizePlan()
+        assert lib.hvlm_resize_plan_host(H, W, 224, 224, C.byref(plan)) == 0
+        nh, nw = restate.clip_resize_output_size(H, W)
+        assert (plan.new_h, plan.new_w) == (nh, nw) and (plan.top, plan.left) == ((nh - 224) // 2, (nw - 224) // 2)
+        tab = (C.c_int32 * plan.table_ints)()
+        assert lib.hvlm_resize_tables_host(C.byref(plan), tab) == 0
+        t = np.array(tab)
+        xb_r, xc_r = restate.resample_table(W, nw)
+        yb_r, yc_r = restate.resample_table(H, nh)
+        xb, rest = t[:448].reshape(224, 2), t[448:]
+        xc, rest = rest[:224 * plan.xk].reshape(224, plan.xk), rest[224 * plan.xk:]
+        yb, yc = rest[:448].reshape(224, 2), rest[448:].reshape(224, plan.yk)
+        assert np.array_equal(xb, xb_r[plan.left:plan.left + 224]) and np.array_equal(xc, xc_r[plan.left:plan.left + 224])
+        assert np.array_equal(yb, yb_r[plan.top:plan.top + 224]) and np.array_equal(yc, yc_r[plan.top:plan.top + 224])
+        assert plan.x_lo == xb[0, 0] and plan.x_lo + plan.x_cols == xb[-1, 0] + xb[-1, 1] <= W
+        need = max(yb[min(y0 + 8, 224) - 1].sum() - yb[y0, 0] for y0 in range(0, 224, 8))
+        assert plan.rows_cap == need
+    assert lib.hvlm_resize_plan_host(100, 100, 224, 300, C.byref(L.ResizePlan())) < 0      # crop larger than the resize
