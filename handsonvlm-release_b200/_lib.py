@@ -22,7 +22,7 @@ SPLICE_FLAG_IM_START_END = 0x100   # OR-able into the splice variant (include/hv
 EPI_BIAS, EPI_BIAS_QUICKGELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 PLAN_ERR_LEN_OVERFLOW, PLAN_ERR_IMG_OVERFLOW, PLAN_ERR_HAND_COUNT, PLAN_ERR_BAD_ID, PLAN_NOT_UNIFORM = 1, 2, 4, 8, 16
 VIT_MAX_LAYERS = 24
-ABI_VERSION = 2
+ABI_VERSION = 3
 STAGES = ["im2col", "patch_gemm", "layernorm", "qkv_gemm", "attention", "outproj_gemm", "fc1_gemm", "fc2_gemm", "pool",
           "gemm", "splice", "gather", "other"]
 
@@ -35,10 +35,14 @@ class _Layer(C.Structure):
                                           "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
 
 
+class _FoldLayer(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("w_qkv_f", "c_qkv", "b_qkv_f", "w_fc1_f", "c_fc1", "b_fc1_f")]
+
+
 class VitLayout(C.Structure):
     _fields_ = [("patch_w", C.c_uint64), ("cls", C.c_uint64), ("pos", C.c_uint64), ("pre_ln_g", C.c_uint64),
                 ("pre_ln_b", C.c_uint64), ("layer", _Layer * VIT_MAX_LAYERS), ("total_bytes", C.c_uint64),
-                ("n_layers", C.c_int32), ("_pad", C.c_int32)]
+                ("n_layers", C.c_int32), ("_pad", C.c_int32), ("fold", _FoldLayer * VIT_MAX_LAYERS)]
 
 
 class ResizePlan(C.Structure):
@@ -59,6 +63,10 @@ SIGNATURES = {
     "hvlm_vit_l14_fwd_open_mlp": (i32, [p, i32, p, i32, p, p, i32, p, p, sz, C.POINTER(C.c_uint64), p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
+    "hvlm_layernorm_1024_stats": (i32, [p, p, p, p, p, p, i32, f32, p]),
+    "hvlm_gemm_ln_fold_bf16": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, f32, p]),
+    "hvlm_gemm_resid_stats": (i32, [p, p, p, p, p, p, i32, i32, p]),
+    "hvlm_vit_set_ln_fold": (i32, [i32]),
     "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, i32, p]),
     "hvlm_vit_attention": (i32, [p, p, i32, p]),
     "hvlm_pool_out_tokens": (i32, [i32, i32]),

@@ -17,6 +17,21 @@
 #include "hvlm_internal.cuh"
 #include "hvlm_ptx.cuh"
 
+// timing probes (tools/fold_probe.py builds variants of the library with these; the defaults are the product)
+#ifndef HVLM_P_ARRIVE
+#define HVLM_P_ARRIVE 1     // 1: cta-scope remote arrive on the leader's accumulator barrier; 0: .release.cluster (MEMBAR.GPU)
+#endif
+#ifndef HVLM_P_EARLY
+#define HVLM_P_EARLY 0      // 1: release the accumulator right after its last tcgen05.ld, before that chunk's math
+                            //    (measured: no gain for fc1, QKV with the folded LayerNorm 109-122 vs 101 us -- off)
+#endif
+#ifndef HVLM_P_NOXB
+#define HVLM_P_NOXB 0       // 1: (WRONG RESULTS, timing only) residual-load producer without the bf16 copy
+#endif
+#ifndef HVLM_P_RL_LONGK
+#define HVLM_P_RL_LONGK 2   // residual-load buffers for K >= 2048 (2: six K stages, one unit of lookahead; 4: five stages, two)
+#endif
+
 namespace hvlm {
 namespace gemm2 {
 
@@ -27,10 +42,13 @@ constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2.
 // G = number of 4-warp epilogue groups (each owns half of the tile's columns when G == 2)
 // RL = "residual load" epilogue: the fp32 residual tile is TMA-LOADED into the staging buffer, the accumulator is added
 //      in shared memory and the sum leaves with a plain TMA store (4 staging buffers: the load runs two units ahead)
-template <int G, bool RL = false>
+// RL = 0: off; 4: four staging buffers, the residual load runs two units ahead (short K: the epilogue is the critical path);
+//      2: two buffers, one unit ahead behind an L2 prefetch of the whole next tile, and the K pipeline keeps its six stages
+//         (long K: the epilogue has slack, the K loop does not -- 4 instead of 5 stages cost the K = 4096 GEMM 20 us)
+template <int G, int RL = 0>
 struct Cfg2 {
-    static constexpr int kStages = (G == 2 || RL) ? 5 : 6;
-    static constexpr int kBufs = RL ? 4 : 2;                     // staging buffers per epilogue group
+    static constexpr int kStages = (G == 2 || RL == 4) ? 5 : 6;
+    static constexpr int kBufs = RL ? RL : 2;                    // staging buffers per epilogue group
     static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * kBufs * (BM * 128) + 1024 + 256;
 };
 constexpr int kABytes = BM * BK * 2;            // 16 KB
@@ -85,7 +103,14 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+#if HVLM_P_ARRIVE
+    // default semantics (.release at CTA scope): what this arrival orders is the thread's own tcgen05.ld (fenced by
+    // tcgen05.fence::before_thread_sync), not generic-proxy memory -- a cluster-scope release compiles to MEMBAR.ALL.GPU,
+    // which waits for every outstanding global access of the thread (ncu: 18 % of the peer CTA's epilogue time)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#else
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
 }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
@@ -170,14 +195,24 @@ struct Sched {
     }
 };
 
-template <int EPI, bool LN, int G, bool RL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2) ? 128 : 0), 1)
+// FOLD = LayerNorm folded into the GEMMs around it (EpiArgs::ln_stats / xb_out):
+//   * consumer (RL == false; QKV / fc1): A holds the un-normalised bf16 rows, B the gamma-scaled weights; the epilogue
+//     applies the row's (mean, rstd), read once per tile from the eight per-128-column partial sums
+//   * producer (RL == true; out_proj / fc2): the residual-load epilogue holds the updated fp32 row values in registers, so
+//     it also writes their bf16 copy (the next GEMM's A operand) and the partial sums -- the LayerNorm kernel between the
+//     two GEMMs (4 KB read + 2 KB write per row) disappears
+template <int EPI, bool LN, int G, int RL, bool FOLD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2 || (RL != 0 && FOLD)) ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_bh, const __grid_constant__ CUtensorMap tma_c, int M, int N,
                      int K, EpiArgs ep, int split_tail) {
     static_assert(epi_is_staged<EPI>() || EPI == EPI_PATCH, "the 2-CTA kernel only implements the smem-staged TMA-store epilogues");
     static_assert(!(LN && G == 2), "the fused-LayerNorm warps and the second epilogue group use the same warp slots");
     static_assert(!RL || (EPI == EPI_RESID_F32 && !LN && G == 1), "residual-load epilogue: fp32 residual GEMM, one group");
+    static_assert(!FOLD || (!LN && (RL || EPI == EPI_QKV_HM || EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16)),
+                  "folded LayerNorm: residual-load producer or a bf16-output consumer");
+    constexpr bool kXb = RL && FOLD;
+    constexpr int kLook = RL / 2;                    // residual-load lookahead in units
     constexpr int kStages = Cfg2<G, RL>::kStages;
     constexpr int kBufs = Cfg2<G, RL>::kBufs;
     extern __shared__ uint8_t smem_raw[];
@@ -193,6 +228,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     uint64_t* tempty_bar = bars + 2 * kStages + 2;   // [2]        epilogues of BOTH CTAs -> MMA (leader's copy is used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     uint64_t* ld_bar = bars + 2 * kStages + 5;       // [4]        RL only: residual tile landed in staging buffer i
+    uint64_t* xfull_bar = ld_bar + 4;                // [4]        RL + FOLD: epilogue (128) -> copy warps: buffer i holds the sums
+    uint64_t* xdone_bar = xfull_bar + 4;             // [4]        RL + FOLD: copy warps (128) -> store warp: buffer i was read
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,8 +255,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 256 * G);   // 128*G epilogue threads in each CTA of the pair
         }
-        if constexpr (RL)
-            for (int i = 0; i < 4; ++i) mbar_init(&ld_bar[i], 1);
+        if constexpr (RL != 0)
+            for (int i = 0; i < 4; ++i) {
+                mbar_init(&ld_bar[i], 1);
+                mbar_init(&xfull_bar[i], 128);
+                mbar_init(&xdone_bar[i], 128);
+            }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot);
@@ -328,11 +369,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 pf_ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
             }
         };
-        auto pf_issue = [&](uint32_t g) {   // load the residual tile of the lookahead unit into buffer g & 3, advance
+        auto pf_issue = [&](uint32_t g) {   // load the residual tile of the lookahead unit into its buffer, advance
             if (pf_v < sched.nv) {
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&ld_bar[g & 3u], kStoreBuf);
-                    tma_load_2d(smem_cg + (g & 3u) * kStoreBuf, &tma_c, &ld_bar[g & 3u], pf_ncol0 + pf_uu * kUnitCols, pf_m0);
+                    const uint32_t b = g & static_cast<uint32_t>(kBufs - 1);
+                    mbar_arrive_expect_tx(&ld_bar[b], kStoreBuf);
+                    tma_load_2d(smem_cg + b * kStoreBuf, &tma_c, &ld_bar[b], pf_ncol0 + pf_uu * kUnitCols, pf_m0);
                 }
                 __syncwarp();
                 if (++pf_uu == pf_units) {
@@ -342,13 +384,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 }
             }
         };
-        if constexpr (RL) {
+        if constexpr (RL != 0) {
             if (store_warp) {
                 pf_tile();
                 pf_issue(0);
-                pf_issue(1);
+                if constexpr (kLook == 2) pf_issue(1);
             }
         }
+        // FOLD consumer: the row's eight (sum, sum of squares) partials are fetched ONE TILE AHEAD (64 bytes per thread from
+        // L2: on the critical path they cost ~0.5 us per tile, which an epilogue-bound short-K GEMM cannot hide)
+        [[maybe_unused]] float4 st_next[4];
+        auto stats_fetch = [&](int v) {
+            if constexpr (FOLD && !RL) {
+                int m_blk = 0, n_blk, half;
+                if (v < sched.nv) sched.decode(v, m_blk, n_blk, half);
+                const int grow = m_blk * 2 * BM + static_cast<int>(rank) * BM + row;
+                const float4* sp = reinterpret_cast<const float4*>(ep.ln_stats + static_cast<size_t>(grow < M ? grow : 0) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_next[j] = __ldcg(sp + j);
+            }
+        };
+        stats_fetch(pair);
         for (int v = pair; v < sched.nv; v += n_pairs) {
             int m_blk, n_blk, half;
             sched.decode(v, m_blk, n_blk, half);
@@ -357,6 +413,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             const int units = half < 0 ? kUnits : kUnits / 2;
             const int u0 = grp * units;
             const int ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
+            [[maybe_unused]] float f_rstd = 1.f, f_nmr = 0.f;      // consumer: this thread's row statistics
+            [[maybe_unused]] float f_s = 0.f, f_ss = 0.f;          // producer: running (sum, sum of squares) of 128 columns
+            if constexpr (FOLD && !RL) {
+                fold_row_stats(st_next, ep.ln_eps, f_rstd, f_nmr);
+                stats_fetch(v + n_pairs);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
@@ -365,12 +427,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 const int u = u0 + uu;
                 uint8_t* buf = smem_cg + (ucount & static_cast<uint32_t>(kBufs - 1)) * kStoreBuf;
                 uint8_t* brow = buf + row * 128;
-                if constexpr (RL) {
+                if constexpr (RL != 0) {
                     if (store_warp) {
-                        // the store of unit ucount-2 has finished reading its buffer == buffer (ucount+2) & 3: refill it
-                        if (elect_one()) bulk_wait_read<1>();
+                        // the store of unit ucount-kLook has finished reading its buffer == buffer (ucount+kLook) % kBufs, and
+                        // (FOLD) so have the copy warps: refill it
+                        if (elect_one()) bulk_wait_read<kLook - 1>();
                         __syncwarp();
-                        pf_issue(ucount + 2u);
+                        if constexpr (kXb && !HVLM_P_NOXB) {
+                            const uint32_t prev = ucount + static_cast<uint32_t>(kLook - kBufs);    // that buffer's last unit
+                            if (ucount + kLook >= static_cast<uint32_t>(kBufs))
+                                mbar_wait(&xdone_bar[prev & static_cast<uint32_t>(kBufs - 1)], (prev / static_cast<uint32_t>(kBufs)) & 1u);
+                        }
+                        pf_issue(ucount + static_cast<uint32_t>(kLook));
                     }
                     // no CTA barrier here: the load barrier below is what says "this buffer holds the residual tile"
                 } else {
@@ -386,10 +454,18 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                     uint32_t r[32];
                     tmem_ld32(t_row + static_cast<uint32_t>(u * kUnitCols + h * 32), r);
                     tmem_ld_wait();
+                    if (HVLM_P_EARLY && uu == units - 1 && h == kUnitCols / 32 - 1) {
+                        // last TMEM read of this accumulator by this group: release it to the (leader's) MMA warp now,
+                        // the values are in registers
+                        tc_fence_before();
+                        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                        else mbar_arrive_cluster(&tempty_bar[acc], 0);
+                    }
                     float v[32];
-                    epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
+                    if constexpr (FOLD && !RL) epilogue_math_fold<EPI>(r, ep.bias, ep.ln_c, n0 + h * 32, f_rstd, f_nmr, v);
+                    else epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
                     if constexpr (RL) {
-                        mbar_wait(&ld_bar[ucount & 3u], (ucount >> 2) & 1u);
+                        mbar_wait(&ld_bar[ucount & static_cast<uint32_t>(kBufs - 1)], (ucount / static_cast<uint32_t>(kBufs)) & 1u);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float4* p4 = reinterpret_cast<float4*>(brow + ((j ^ sw) << 4));
@@ -399,6 +475,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                             x.z += v[4 * j + 2];
                             x.w += v[4 * j + 3];
                             *p4 = x;
+                            if constexpr (FOLD) {
+                                f_s += (x.x + x.y) + (x.z + x.w);
+                                f_ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, f_ss))));
+                            }
+                        }
+                        if constexpr (FOLD) {
+                            // every 4th unit (32 columns each) closes a 128-column block of the row statistics
+                            if ((u & 3) == 3) {
+                                if (m0 + row < M)
+                                    *reinterpret_cast<float2*>(ep.stats_out + static_cast<size_t>(m0 + row) * 16 + (n0 >> 7) * 2) =
+                                        make_float2(f_s, f_ss);
+                                f_s = f_ss = 0.f;
+                            }
                         }
                     } else if constexpr (kF32) {
 #pragma unroll
@@ -417,7 +506,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         }
                     }
                 }
-                if (uu == units - 1) {
+                if constexpr (kXb && !HVLM_P_NOXB) mbar_arrive(&xfull_bar[ucount & static_cast<uint32_t>(kBufs - 1)]);
+                if (!HVLM_P_EARLY && uu == units - 1) {
                     // last TMEM read of this accumulator by this group: release it to the (leader's) MMA warp
                     tc_fence_before();
                     if (rank == 0) mbar_arrive(&tempty_bar[acc]);
@@ -477,6 +567,46 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             __syncwarp();
         }
     } else {
+        // ===================== copy warps (6..9), only when RL + FOLD: the bf16 twin of every residual unit =====================
+        // They read the fp32 sums back from the staging buffer TRANSPOSED -- 8 lanes take one row's 128 bytes (conflict-free
+        // under the 128-byte swizzle) and write its 64 bf16 bytes contiguously, 4 rows per instruction -- off the epilogue
+        // warps' critical path.  (Measured per out_proj call, stand-alone: this read-back inside the epilogue warps +15 us;
+        // 16-byte stores from one row per lane +23 us; a second TMA store needs staging memory the K pipeline cannot
+        // spare: 4 stages instead of 5 cost the K = 4096 GEMM 20 us.)
+        if constexpr (kXb && !HVLM_P_NOXB) {
+            constexpr int kUnits = BN / 32;
+            const int cw = warp - 6;
+            const int cj = lane & 7;
+            uint32_t ucount = 0;
+            for (int v = pair; v < sched.nv; v += n_pairs) {
+                int m_blk, n_blk, half;
+                sched.decode(v, m_blk, n_blk, half);
+                const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+                const int units = half < 0 ? kUnits : kUnits / 2;
+                const int ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
+#pragma unroll 1
+                for (int uu = 0; uu < units; ++uu, ++ucount) {
+                    const uint32_t b = ucount & static_cast<uint32_t>(kBufs - 1);
+                    const uint8_t* buf = smem_c + b * kStoreBuf;
+                    mbar_wait(&xfull_bar[b], (ucount / static_cast<uint32_t>(kBufs)) & 1u);
+                    __nv_bfloat16* xo = static_cast<__nv_bfloat16*>(ep.xb_out) + ncol0 + uu * 32 + 4 * cj;
+                    float4 x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = cw * 32 + 4 * i + (lane >> 3);
+                        x[i] = *reinterpret_cast<const float4*>(buf + rr * 128 + ((cj ^ (rr & 7)) << 4));
+                    }
+                    mbar_arrive(&xdone_bar[b]);       // the values are in registers: the buffer may be refilled
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = cw * 32 + 4 * i + (lane >> 3);
+                        if (m0 + rr < M)
+                            *reinterpret_cast<uint2*>(xo + static_cast<size_t>(m0 + rr) * N) =
+                                make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
+                    }
+                }
+            }
+        }
         // ===================== LayerNorm warps (6..9), only when LN: normalise finished 128-row blocks =====================
         if constexpr (LN) {
             const int lw = warp - 6;
@@ -510,7 +640,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     if (warp == 1) tmem_dealloc_2sm(tmem_base);
 }
 
-template <int EPI, bool LN = false, int G = 1, bool RL = false>
+template <int EPI, bool LN = false, int G = 1, int RL = 0, bool FOLD = false>
 static int launch_two(const void* A, const void* B, int M, int N, int K, const EpiArgs& ep, cudaStream_t s) {
     CUtensorMap ta, tb, tbh, tc;
     {
@@ -558,7 +688,7 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
         }
         if (rc) return rc;
     }
-    auto kern = gemm2_tcgen05_kernel<EPI, LN, G, RL>;
+    auto kern = gemm2_tcgen05_kernel<EPI, LN, G, RL, FOLD>;
     constexpr int kSmemBytes = Cfg2<G, RL>::kSmemBytes;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -578,7 +708,7 @@ static int launch_two(const void* A, const void* B, int M, int N, int K, const E
     int pairs = num_sms() / 2;
     const int want = allow_split ? 2 * tiles : tiles;      // few tiles: cut all of them in two to occupy more pairs
     if (want < pairs) pairs = want;
-    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + ((LN || G == 2) ? 128 : 0)), kSmemBytes, s, ta, tb, tbh, tc, M, N, K, ep,
+    if (launch_pdl(kern, dim3(2 * pairs), dim3(kThreads + ((LN || G == 2 || (RL != 0 && FOLD)) ? 128 : 0)), kSmemBytes, s, ta, tb, tbh, tc, M, N, K, ep,
                    allow_split) != cudaSuccess) {
         cudaGetLastError();
         return HVLM_ERR_CUDA;
@@ -604,13 +734,34 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
         const char* e = getenv("HVLM_RESID_LOAD_MAXK");
         return e ? atoi(e) : 0;
     }();
-    if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
-        return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
     // HVLM_QKV_EPI_GROUPS=2: the same second epilogue group for the QKV GEMM (A/B runs; see DESIGN.md for the outcome)
     static const bool qkv_two = []() {
         const char* e = getenv("HVLM_QKV_EPI_GROUPS");
         return e && e[0] == '2';
     }();
+    if (ep.ln_stats != nullptr) {
+        // LayerNorm folded into this GEMM (consumer side)
+        if (K != 1024 || !ep.ln_c || !ep.bias || !aligned16(ep.ln_c) || !aligned16(ep.ln_stats)) return HVLM_ERR_BAD_ARG;
+        switch (epi) {
+            case EPI_QKV_HM:
+                return qkv_two ? launch_two<EPI_QKV_HM, false, 2, false, true>(A, B, M, N, K, ep, s)
+                               : launch_two<EPI_QKV_HM, false, 1, false, true>(A, B, M, N, K, ep, s);
+            case EPI_BIAS_BF16: return launch_two<EPI_BIAS_BF16, false, 1, false, true>(A, B, M, N, K, ep, s);
+            case EPI_GELU_BF16:
+                return two_groups ? launch_two<EPI_GELU_BF16, false, 2, false, true>(A, B, M, N, K, ep, s)
+                                  : launch_two<EPI_GELU_BF16, false, 1, false, true>(A, B, M, N, K, ep, s);
+            default: return HVLM_ERR_UNSUPPORTED;
+        }
+    }
+    if (ep.xb_out != nullptr) {
+        // producer side of the fold: residual-load epilogue + bf16 copy + row statistics
+        if (epi != EPI_RESID_F32 || N != 1024 || !ep.stats_out || !aligned16(ep.xb_out) || !aligned16(ep.stats_out))
+            return HVLM_ERR_BAD_ARG;
+        if (K >= 2048) return launch_two<EPI_RESID_F32, false, 1, HVLM_P_RL_LONGK, true>(A, B, M, N, K, ep, s);
+        return launch_two<EPI_RESID_F32, false, 1, 4, true>(A, B, M, N, K, ep, s);
+    }
+    if (two_groups && ep.ln_out == nullptr && epi == EPI_GELU_BF16)
+        return launch_two<EPI_GELU_BF16, false, 2>(A, B, M, N, K, ep, s);
     if (qkv_two && epi == EPI_QKV_HM) return launch_two<EPI_QKV_HM, false, 2>(A, B, M, N, K, ep, s);
     switch (epi) {
         case EPI_BIAS_BF16: return launch_two<EPI_BIAS_BF16>(A, B, M, N, K, ep, s);
@@ -629,7 +780,7 @@ int launch_gemm_2cta(int epi, const void* A, const void* B, int M, int N, int K,
             // with a plain TMA store.  Correct (same tests), but measured SLOWER on B200, same box, 100 frames: out_proj
             // 74.3 vs 66.7 us per call, step 14.91 vs 14.52 ms -- the extra 32 KB of shared-memory traffic per unit (TMA
             // write + read-modify-write) competes with the tensor cores' operand reads; the L2-side reduce-add stays.
-            if (K <= resid_load_maxk) return launch_two<EPI_RESID_F32, false, 1, true>(A, B, M, N, K, ep, s);
+            if (K <= resid_load_maxk) return launch_two<EPI_RESID_F32, false, 1, 4>(A, B, M, N, K, ep, s);
             return launch_two<EPI_RESID_F32>(A, B, M, N, K, ep, s);
         case EPI_QKV_HM: return launch_two<EPI_QKV_HM>(A, B, M, N, K, ep, s);
         default: return HVLM_ERR_UNSUPPORTED;

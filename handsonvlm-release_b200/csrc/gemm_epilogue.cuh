@@ -46,4 +46,42 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], const f
     }
 }
 
+// LayerNorm folded into the GEMM (see EpiArgs::ln_stats): v = rstd * acc + (bias[n] - mean * rstd * c[n]) -> (quick-GELU)
+template <int EPI>
+__device__ __forceinline__ void epilogue_math_fold(const uint32_t (&acc)[32], const float* __restrict__ bias,
+                                                   const float* __restrict__ csum, int n0, float rstd, float nmr,
+                                                   float (&v)[32]) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
+    const float4* c4 = reinterpret_cast<const float4*>(csum + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        const float4 c = __ldg(c4 + j);
+        // packed fp32x2 FMAs: the epilogue warps are alone on their schedulers, instruction count is what they pay for
+        float t0, t1, t2, t3;
+        ffma2(t0, t1, nmr, nmr, c.x, c.y, b.x, b.y);
+        ffma2(t2, t3, nmr, nmr, c.z, c.w, b.z, b.w);
+        ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(acc[4 * j + 0]), __uint_as_float(acc[4 * j + 1]), rstd, rstd, t0, t1);
+        ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]), rstd, rstd, t2, t3);
+    }
+    if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_F32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    }
+}
+
+// (mean, rstd) of a 1024-wide row from its eight (sum, sum of squares) partials; returns rstd and nmr = -mean * rstd
+__device__ __forceinline__ void fold_row_stats(const float4 (&st)[4], float eps, float& rstd, float& nmr) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s += st[j].x + st[j].z;
+        ss += st[j].y + st[j].w;
+    }
+    const float mean = s * (1.0f / 1024.0f);
+    const float var = fmaxf(fmaf(-mean, mean, ss * (1.0f / 1024.0f)), 0.f);
+    rstd = rsqrtf(var + eps);
+    nmr = -mean * rstd;
+}
+
 }  // namespace hvlm

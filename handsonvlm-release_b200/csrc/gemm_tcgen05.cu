@@ -40,7 +40,7 @@ static void load_encode() {
 }
 
 static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     std::call_once(g_encode_once, load_encode);
     if (!g_encode) return HVLM_ERR_CUDA;
     cuuint64_t gdim[5];
@@ -55,7 +55,7 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base,
     }
     CUresult r = g_encode(out, dt, static_cast<cuuint32_t>(rank),
                           const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS && getenv("HVLM_DEBUG"))
         fprintf(stderr, "[hvlm] cuTensorMapEncodeTiled failed: CUresult %d (rank %d)\n", static_cast<int>(r), rank);
@@ -476,6 +476,7 @@ int launch_gemm(int epi, const void* A, const void* B, int M, int N, int K, cons
         const int rc2 = launch_gemm_2cta(epi, A, B, M, N, K, ep, s);
         if (rc2 != HVLM_ERR_UNSUPPORTED) return rc2;
     }
+    if (ep.ln_stats != nullptr || ep.xb_out != nullptr) return HVLM_ERR_UNSUPPORTED;   // the folded LayerNorm lives in the 2-CTA kernel
     const bool wide = (N % 256) == 0;
 #define HVLM_GEMM_CASE(E)                                                         \
     case E:                                                                       \
@@ -534,4 +535,39 @@ extern "C" int hvlm_gemm_bf16(const void* A, const void* B, const float* bias, c
     }
     StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
     return launch_gemm(epi, A, B, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hvlm_gemm_ln_fold_bf16(const void* xb, const float* stats, const void* w_f, const float* c, const float* b_f,
+                                      void* out, int M, int N, int epilogue, int qkv_hm, float eps, void* stream) {
+    using namespace hvlm;
+    if (!xb || !stats || !w_f || !c || !b_f || !out || M <= 0 || N <= 0) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(out) || !aligned16(stats) || !aligned16(c) || !aligned16(b_f)) return HVLM_ERR_ALIGN;
+    if ((N % 256) != 0 || (qkv_hm && N != 3072)) return HVLM_ERR_BAD_SHAPE;
+    int epi;
+    if (epilogue == HVLM_EPI_BIAS) epi = qkv_hm ? EPI_QKV_HM : EPI_BIAS_BF16;
+    else if (epilogue == HVLM_EPI_BIAS_QUICKGELU && !qkv_hm) epi = EPI_GELU_BF16;
+    else return HVLM_ERR_BAD_ARG;
+    EpiArgs ep;
+    ep.bias = b_f;
+    ep.ln_c = c;
+    ep.ln_stats = stats;
+    ep.ln_eps = eps;
+    ep.out = out;
+    StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
+    return launch_gemm(epi, xb, w_f, M, N, 1024, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, void* xb_out,
+                                     float* stats_out, int M, int K, void* stream) {
+    using namespace hvlm;
+    if (!hidden || !xb_out || !stats_out) return HVLM_ERR_BAD_ARG;
+    if (!aligned16(hidden) || !aligned16(xb_out) || !aligned16(stats_out) || (bias && !aligned16(bias))) return HVLM_ERR_ALIGN;
+    EpiArgs ep;
+    ep.bias = bias;
+    ep.resid = hidden;
+    ep.out = hidden;
+    ep.xb_out = xb_out;
+    ep.stats_out = stats_out;
+    StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
+    return launch_gemm(EPI_RESID_F32, A, B, M, 1024, K, ep, static_cast<cudaStream_t>(stream));
 }

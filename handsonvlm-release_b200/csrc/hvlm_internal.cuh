@@ -34,6 +34,17 @@ struct EpiArgs {
     const float* ln_beta = nullptr;
     void* ln_out = nullptr;        // bf16 [M,1024]
     int32_t* ln_count = nullptr;   // int32 [ceil(M/128)], zero on entry, zero again on exit
+    // LayerNorm FOLDED into the GEMM that consumes it (2-CTA kernel; EPI_QKV_HM / EPI_BIAS_BF16 / EPI_GELU_BF16, K == 1024):
+    //   LN(x) W^T + b  =  rstd_i * (bf16(x) (gamma*W)^T - mean_i * c) + (b + W beta),   c[n] = sum_k (gamma*W)[n,k]
+    // A = bf16(x) (un-normalised rows), B = bf16(gamma*W), bias = b + W beta, and the epilogue applies the row's
+    // (mean, rstd) computed from `ln_stats`.
+    const float* ln_c = nullptr;       // f32 [N]
+    const float* ln_stats = nullptr;   // f32 [M][8][2]: (sum, sum of squares) of x over each 128-column block of the row
+    float ln_eps = 1e-5f;
+    // the producer side of the fold (EPI_RESID_F32, N == 1024): the epilogue LOADS the residual tile, so it can also emit
+    // the bf16 copy of the updated rows and their per-128-column statistics for the next folded GEMM
+    void* xb_out = nullptr;            // bf16 [M,1024]
+    float* stats_out = nullptr;        // f32 [M][8][2]
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue.  Returns an hvlm_status.

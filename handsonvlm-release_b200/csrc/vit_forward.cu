@@ -5,15 +5,18 @@
 // run (23 of 24 for select_layer=-2); no hidden-state list is kept; the fp32 residual stream is the single
 // [n,257,1024] output buffer and every GEMM epilogue reads/writes it in place.
 //
-// Per layer (7 launches):  LN1 -> QKV GEMM (column-block-major q|k|v [48][M][64] via 3-D TMA stores) -> attention -> out_proj GEMM (+residual)
-//                          -> LN2 -> fc1 GEMM (+quick-GELU) -> fc2 GEMM (+residual)
+// Per layer (5 launches; default):  QKV GEMM (LN1 folded in; column-block-major q|k|v [48][M][64] via 3-D TMA stores) -> attention
+//                          -> out_proj GEMM (+residual; emits bf16 rows + row statistics) -> fc1 GEMM (LN2 folded in, +quick-GELU)
+//                          -> fc2 GEMM (+residual; emits bf16 rows + row statistics)
+// HVLM_LN_FOLD=0 / hvlm_vit_set_ln_fold(0) (7 launches):  LN1 -> QKV GEMM -> attention -> out_proj GEMM (+residual) -> LN2 -> fc1 GEMM -> fc2 GEMM
 #include <cstdlib>
 
 #include "hvlm_internal.cuh"
 
 namespace hvlm {
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s, int reverse, const float* add_rows = nullptr, int add_period = 1);
+                     cudaStream_t s, int reverse, const float* add_rows = nullptr, int add_period = 1, void* xb_out = nullptr,
+                     float* stats_out = nullptr);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
 int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv, int n_frames, void* A, const float* cls,
@@ -23,7 +26,7 @@ int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct VitWorkspace {
-    uint64_t a_patch, y, qkv, attn, f1, ln_count, total;
+    uint64_t a_patch, y, qkv, attn, f1, ln_count, stats, total;
 };
 
 static VitWorkspace vit_workspace(int n_frames) {
@@ -42,6 +45,7 @@ static VitWorkspace vit_workspace(int n_frames) {
     w.attn = take(M * 1024 * 2);
     w.f1 = take(M * 4096 * 2);
     w.ln_count = take(((M + 127) / 128) * 4);
+    w.stats = take(M * 16 * 4);      // folded LayerNorm: (sum, sum of squares) per row and 128-column block
     w.total = off;
     return w;
 }
@@ -77,10 +81,38 @@ extern "C" int hvlm_vit_l14_layout(int n_layers, hvlm_vit_layout* L) {
         y.b_fc1 = take(4096 * 4);
         y.w_fc2 = take(1024ull * 4096 * 2);
         y.b_fc2 = take(1024 * 4);
+        auto& f = L->fold[l];       // ABI 3: the folded-LayerNorm operands of the layer (per layer, so that a blob packed
+        f.w_qkv_f = take(3072ull * 1024 * 2);   // for n layers still runs any prefix of them)
+        f.c_qkv = take(3072 * 4);
+        f.b_qkv_f = take(3072 * 4);
+        f.w_fc1_f = take(4096ull * 1024 * 2);
+        f.c_fc1 = take(4096 * 4);
+        f.b_fc1_f = take(4096 * 4);
     }
     L->total_bytes = off;
     L->n_layers = n_layers;
     return HVLM_OK;
+}
+
+namespace hvlm {
+static int g_ln_fold = -1;    // -1: not decided yet (environment), 0 / 1
+static int ln_fold_setting() {
+    if (g_ln_fold < 0) {
+        const char* e = getenv("HVLM_LN_FOLD");
+        const char* one = getenv("HVLM_GEMM_1CTA");     // the fold lives in the 2-CTA kernel only
+        g_ln_fold = ((e && e[0] == '0') || (one && one[0] == '1')) ? 0 : 1;
+    }
+    return g_ln_fold;
+}
+}  // namespace hvlm
+
+extern "C" int hvlm_vit_set_ln_fold(int on) {
+    const int prev = hvlm::ln_fold_setting();
+    if (on >= 0) {
+        const char* one = getenv("HVLM_GEMM_1CTA");
+        hvlm::g_ln_fold = (on != 0 && !(one && one[0] == '1')) ? 1 : 0;
+    }
+    return prev;
 }
 
 extern "C" size_t hvlm_vit_l14_workspace_bytes(int n_frames) {
@@ -129,6 +161,8 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         const char* e = getenv("HVLM_LN_FUSION");
         return e && e[0] == '1';
     }();
+    const bool fold = !fuse_ln && ln_fold_setting() != 0 && n_layers_run > 0;
+    float* stats = reinterpret_cast<float*>(w8 + ws.stats);
     int32_t* ln_count = reinterpret_cast<int32_t*>(w8 + ws.ln_count);
     if (fuse_ln && cudaMemsetAsync(ln_count, 0, static_cast<size_t>((M + 127) / 128) * 4, s) != cudaSuccess) return HVLM_ERR_CUDA;
 
@@ -152,24 +186,30 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
     {
         StageTimer st(HVLM_STAGE_LAYERNORM, s);
         // + position embedding (tokens 1..256; the CLS row got pos[0] from im2col), then pre_layrnorm, in place
+        // (folded LayerNorms: it also writes the bf16 rows + row statistics the first QKV GEMM consumes)
         rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1, f32(L.pos),
-                              HVLM_VIT_TOKENS);
+                              HVLM_VIT_TOKENS, fold ? w8 + ws.y : nullptr, fold ? stats : nullptr);
     }
     if (rc) return rc;
 
     for (int l = 0; l < n_layers_run; ++l) {
         const auto& y = L.layer[l];
-        if (!fuse_ln || l == 0) {   // with fusion, LN1 of layer l > 0 was produced by fc2 of layer l-1
+        const auto& yf = L.fold[l];
+        if (!fold && (!fuse_ln || l == 0)) {   // with fusion, LN1 of layer l > 0 was produced by fc2 of layer l-1
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 0);
             if (rc) return rc;
         }
         {
             EpiArgs ep;
-            ep.bias = f32(y.b_qkv);
+            ep.bias = f32(fold ? yf.b_qkv_f : y.b_qkv);
             ep.out = w8 + ws.qkv;
+            if (fold) {      // LN1 folded in: A = bf16 residual rows, B = gamma-scaled weights
+                ep.ln_c = f32(yf.c_qkv);
+                ep.ln_stats = stats;
+            }
             StageTimer st(HVLM_STAGE_QKV_GEMM, s);
-            rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + y.w_qkv, M, 3072, 1024, ep, s);
+            rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + (fold ? yf.w_qkv_f : y.w_qkv), M, 3072, 1024, ep, s);
             if (rc) return rc;
         }
         {
@@ -188,21 +228,29 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
                 ep.ln_out = w8 + ws.y;
                 ep.ln_count = ln_count;
             }
+            if (fold) {      // feeds the folded LN2 of fc1
+                ep.xb_out = w8 + ws.y;
+                ep.stats_out = stats;
+            }
             StageTimer st(HVLM_STAGE_OUTPROJ_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.attn, wb + y.w_o, M, 1024, 1024, ep, s);
             if (rc) return rc;
         }
-        if (!fuse_ln) {
+        if (!fuse_ln && !fold) {
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 1);
             if (rc) return rc;
         }
         {
             EpiArgs ep;
-            ep.bias = f32(y.b_fc1);
+            ep.bias = f32(fold ? yf.b_fc1_f : y.b_fc1);
             ep.out = w8 + ws.f1;
+            if (fold) {
+                ep.ln_c = f32(yf.c_fc1);
+                ep.ln_stats = stats;
+            }
             StageTimer st(HVLM_STAGE_FC1_GEMM, s);
-            rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + y.w_fc1, M, 4096, 1024, ep, s);
+            rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + (fold ? yf.w_fc1_f : y.w_fc1), M, 4096, 1024, ep, s);
             if (rc) return rc;
         }
         if (open_last_mlp && l + 1 == n_layers_run) break;   // the caller applies fc2 after pooling (it is linear)
@@ -217,6 +265,10 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
                 ep.ln_beta = f32(L.layer[l + 1].ln1_b);
                 ep.ln_out = w8 + ws.y;
                 ep.ln_count = ln_count;
+            }
+            if (fold && l + 1 < n_layers_run) {      // feeds the folded LN1 of the next layer (nobody reads them after the last)
+                ep.xb_out = w8 + ws.y;
+                ep.stats_out = stats;
             }
             StageTimer st(HVLM_STAGE_FC2_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.f1, wb + y.w_fc2, M, 1024, 4096, ep, s);

@@ -297,6 +297,55 @@ def layernorm_1024(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, out_dtype=
     return out
 
 
+def layernorm_1024_stats(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps=1e-5):
+    """LayerNorm with fp32 output plus what a folded GEMM consumes next: (out f32, bf16(out), stats f32 [rows,8,2])."""
+    _need_cuda(x, g, b)
+    ensure_device()
+    x = x.contiguous()
+    rows = x.numel() // 1024
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    xb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty(rows, 8, 2, dtype=torch.float32, device=x.device)
+    L.check(L.lib().hvlm_layernorm_1024_stats(_p(x), _p(g), _p(b), _p(out), _p(xb), _p(stats), rows, eps, _stream()),
+            "hvlm_layernorm_1024_stats")
+    return out, xb, stats
+
+
+def gemm_ln_fold(xb: torch.Tensor, stats: torch.Tensor, w_f: torch.Tensor, c: torch.Tensor, b_f: torch.Tensor, *,
+                 epilogue: str = "bias", qkv_hm: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm folded into its consumer GEMM (hvlm_gemm_ln_fold_bf16): xb bf16 [M,1024] un-normalised rows, stats
+    [M,8,2], w_f bf16 [N,1024] = gamma*W, c [N] its row sums, b_f [N] = b + W beta -> bf16 [M,N] (or [48,M,64])."""
+    _need_cuda(xb, stats, w_f, c, b_f)
+    ensure_device()
+    M, N = xb.shape[0], w_f.shape[0]
+    assert xb.dtype == torch.bfloat16 and w_f.dtype == torch.bfloat16 and xb.shape[1] == 1024 and w_f.shape[1] == 1024
+    assert stats.dtype == torch.float32 and stats.numel() == M * 16 and stats.is_contiguous()
+    out = torch.empty((48, M, 64) if qkv_hm else (M, N), dtype=torch.bfloat16, device=xb.device)
+    L.check(L.lib().hvlm_gemm_ln_fold_bf16(_p(xb.contiguous()), _p(stats), _p(w_f.contiguous()), _p(c), _p(b_f), _p(out), M, N,
+                                           {"bias": L.EPI_BIAS, "quick_gelu": L.EPI_BIAS_QUICKGELU}[epilogue], int(qkv_hm), eps,
+                                           _stream()), "hvlm_gemm_ln_fold_bf16")
+    return out
+
+
+def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], hidden: torch.Tensor):
+    """hidden f32 [M,1024] += a w^T + bias IN PLACE; returns (bf16(hidden), stats [M,8,2]) from the same epilogue."""
+    _need_cuda(a, w, hidden)
+    ensure_device()
+    M, K = a.shape
+    assert hidden.dtype == torch.float32 and tuple(hidden.shape) == (M, 1024) and hidden.is_contiguous()
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and tuple(w.shape) == (1024, K)
+    xb = torch.empty(M, 1024, dtype=torch.bfloat16, device=a.device)
+    stats = torch.empty(M, 8, 2, dtype=torch.float32, device=a.device)
+    L.check(L.lib().hvlm_gemm_resid_stats(_p(a.contiguous()), _p(w.contiguous()), _p(bias), _p(hidden), _p(xb), _p(stats), M, K,
+                                          _stream()), "hvlm_gemm_resid_stats")
+    return xb, stats
+
+
+def vit_set_ln_fold(on: int) -> int:
+    """Process-wide switch of the tower's folded LayerNorms (hvlm_vit_set_ln_fold); returns the previous setting."""
+    return int(L.lib().hvlm_vit_set_ln_fold(int(on)))
+
+
 def vit_qkv(y: torch.Tensor, w_qkv: torch.Tensor, b_qkv: torch.Tensor, n_frames: int) -> torch.Tensor:
     """y bf16 [M=n_frames*257,1024] -> qkv column-block-major bf16 [48, M, 64] (q0..15|k0..15|v0..15)."""
     _need_cuda(y, w_qkv, b_qkv)

@@ -4,6 +4,10 @@ State-dict keys are the ones HuggingFace's ``CLIPVisionModel`` uses (the model t
 llava/model/multimodal_encoder/clip_encoder.py:24), so a real ``openai/clip-vit-large-patch14`` checkpoint loads
 unchanged.  q_proj weight/bias are pre-multiplied by 64^-1/2 (a power of two: exact in bf16), which removes the
 score scaling from the attention kernel.
+
+ABI 3 adds the operands of the FOLDED LayerNorms (``hvlm_vit_layout.fold``): the tower runs LN1 / LN2 inside the QKV / fc1
+GEMMs, ``LN(x) W^T + b = rstd * (bf16(x) (gamma*W)^T - mean * c) + (b + W beta)``, so per layer the blob also holds
+``bf16(gamma*W)`` (rounded once, from the fp32 weights), ``c`` = the row sums of those rounded weights, and ``b + W beta``.
 """
 from __future__ import annotations
 
@@ -20,6 +24,16 @@ def vit_layout(n_layers: int) -> L.VitLayout:
     lay = L.VitLayout()
     L.check(L.lib().hvlm_vit_l14_layout(n_layers, C.byref(lay)), "hvlm_vit_l14_layout")
     return lay
+
+
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """Operands of ``LN(x) W^T + b`` with the LayerNorm folded into the GEMM (fp32 in):
+    (bf16(gamma * W) [N,K], c [N] = row sums of the ROUNDED folded weights, b + W beta [N])."""
+    w = w.detach().to("cpu", torch.float32)
+    w_f = (w * gamma.to("cpu", torch.float32).unsqueeze(0)).to(torch.bfloat16)
+    c = w_f.to(torch.float64).sum(1).to(torch.float32)
+    b_f = (b.detach().to("cpu", torch.float64) + w.to(torch.float64) @ beta.to("cpu", torch.float64)).to(torch.float32)
+    return w_f, c, b_f
 
 
 def pack_vit_weights(sd: dict, n_layers: int = 24, device=None) -> torch.Tensor:
@@ -71,6 +85,15 @@ def pack_vit_weights(sd: dict, n_layers: int = 24, device=None) -> torch.Tensor:
         put(y.b_fc1, sd[q + "mlp.fc1.bias"], torch.float32)
         put(y.w_fc2, sd[q + "mlp.fc2.weight"], torch.bfloat16)
         put(y.b_fc2, sd[q + "mlp.fc2.bias"], torch.float32)
+        f = lay.fold[l]
+        for w, b, g, beta, o_w, o_c, o_b in (
+                (w_qkv, b_qkv, sd[q + "layer_norm1.weight"], sd[q + "layer_norm1.bias"], f.w_qkv_f, f.c_qkv, f.b_qkv_f),
+                (sd[q + "mlp.fc1.weight"].detach().float(), sd[q + "mlp.fc1.bias"].detach().float(),
+                 sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"], f.w_fc1_f, f.c_fc1, f.b_fc1_f)):
+            w_f, c, b_f = fold_layernorm(w, b, g.detach().float(), beta.detach().float())
+            put(o_w, w_f, torch.bfloat16)
+            put(o_c, c, torch.float32)
+            put(o_b, b_f, torch.float32)
     blob_layers = n_layers
     if device is not None:
         blob = blob.to(device)

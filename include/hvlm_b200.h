@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HVLM_ABI_VERSION 2
+#define HVLM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HVLM_API __attribute__((visibility("default")))
@@ -126,6 +126,16 @@ typedef struct {
     uint64_t total_bytes;
     int32_t n_layers;
     int32_t _pad;
+    /* ABI 3: LayerNorm folded into the GEMM that consumes it (see hvlm_gemm_ln_fold_bf16).  For LN(x) W^T + b with
+     * LN(x) = (x - mean) * rstd * gamma + beta the host also packs, per layer and for both LayerNorms:
+     *   w_*_f  bf16 [N,1024]  round(gamma[k] * W[n,k])                (from the fp32 master weights: one rounding)
+     *   c_*    f32  [N]       sum_k float(w_*_f[n,k])                 (of the ROUNDED folded weights)
+     *   b_*_f  f32  [N]       b[n] + sum_k beta[k] * W[n,k]
+     * (qkv: W, b are the q|k|v rows with q pre-scaled like w_qkv / b_qkv.) */
+    struct {
+        uint64_t w_qkv_f, c_qkv, b_qkv_f;
+        uint64_t w_fc1_f, c_fc1, b_fc1_f;
+    } fold[HVLM_VIT_MAX_LAYERS];
 } hvlm_vit_layout;
 
 HVLM_API int hvlm_vit_l14_layout(int n_layers, hvlm_vit_layout* out_host);
@@ -156,9 +166,33 @@ HVLM_API int hvlm_vit_l14_fwd_open_mlp(const void* weight_blob, int n_layers_run
 /* hidden f32 [n,257,1024] -> feats [n,256,1024] (drop CLS) cast to out_dtype (clip_encoder.py:31-32,49). */
 HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls, void* stream);
 
+/* The tower runs with its 46 per-layer LayerNorm launches folded into the GEMMs around them (default; the environment
+ * variable HVLM_LN_FOLD=0 or this call with on = 0 restores the stand-alone LayerNorm kernels; on < 0 only queries).
+ * Process-wide switch, returns the previous setting.  Both settings produce the same tower within bf16-operand rounding
+ * (same operand precision: the GEMM reads bf16(x) and bf16(gamma*W) instead of bf16(LN(x)) and bf16(W)). */
+HVLM_API int hvlm_vit_set_ln_fold(int on);
+
 /* building blocks of the tower, exported for per-stage parity tests */
 HVLM_API int hvlm_layernorm_1024(const float* x, const float* gamma, const float* beta, void* out, int rows, int out_dtype,
                         float eps, void* stream);
+/* The same LayerNorm with f32 output `out` [rows,1024] (may alias x) that also emits what a folded GEMM consumes next:
+ * xb_out bf16 [rows,1024] = bf16(out) and stats_out f32 [rows][8][2] = (sum, sum of squares) of `out` per row
+ * (block 0 carries the whole row, blocks 1..7 are zero).  This is the tower's pre_layrnorm. */
+HVLM_API int hvlm_layernorm_1024_stats(const float* x, const float* gamma, const float* beta, float* out, void* xb_out,
+                                       float* stats_out, int rows, float eps, void* stream);
+/* LayerNorm folded into its consumer GEMM (replaces LayerNorm + Linear of HF CLIPEncoderLayer, modeling_clip.py, as run by
+ * clip_encoder.py:39-51):   out[i,n] = act( rstd_i * (sum_k xb[i,k] w_f[n,k] - mean_i * c[n]) + b_f[n] )
+ *   xb     bf16 [M,1024]  the un-normalised rows;  stats f32 [M][8][2] their (sum, sum of squares) per 128-column block
+ *   w_f, c, b_f           as described at hvlm_vit_layout.fold;  N % 256 == 0, K = 1024
+ *   epilogue              HVLM_EPI_BIAS or HVLM_EPI_BIAS_QUICKGELU, bf16 output [M,N];  qkv_hm != 0 (N = 3072, bias
+ *                         epilogue): column-block-major [48][M][64] output as hvlm_vit_qkv_gemm */
+HVLM_API int hvlm_gemm_ln_fold_bf16(const void* xb, const float* stats, const void* w_f, const float* c, const float* b_f,
+                                    void* out, int M, int N, int epilogue, int qkv_hm, float eps, void* stream);
+/* Residual GEMM that feeds a folded LayerNorm:  hidden[M,1024] (f32, in place) += A[M,K] B[1024,K]^T + bias, and the same
+ * epilogue writes xb_out = bf16(hidden) and stats_out (layout above).  hidden equals what hvlm_gemm_bf16 with
+ * HVLM_EPI_BIAS_RESIDUAL computes, bit for bit. */
+HVLM_API int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, void* xb_out,
+                                   float* stats_out, int M, int K, void* stream);
 /* y bf16 [M = n_frames*257, 1024] (LN1 output) -> qkv bf16 COLUMN-BLOCK-MAJOR [48][M][64]: column blocks
  * q0..q15 | k0..k15 | v0..v15 of (y W_qkv^T + b); q carries the 64^-1/2 scale (folded into the packed weights).
  * Every (frame, head) operand is a contiguous [257][64] block. */

@@ -29,9 +29,25 @@ from .synth import HAND_TRAJ_TOKEN_ID, IGNORE_INDEX, IMAGE_TOKEN_INDEX, VIT_L14,
 def _r(x: torch.Tensor, emulate: str | None) -> torch.Tensor:
     """Round a GEMM operand to bf16 (debug regime that mirrors the CUDA path's operand
     precision); identity in the fp32 oracle regime."""
-    if emulate == "bf16":
+    if emulate in ("bf16", "bf16_fold"):
         return x.to(torch.bfloat16).to(torch.float32)
     return x
+
+
+def folded_layernorm_linear(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, W: torch.Tensor, b: torch.Tensor,
+                            eps: float = 1e-5) -> torch.Tensor:
+    """``LayerNorm(h) W^T + b`` in the arithmetic of the CUDA path's FOLDED LayerNorm (debug regime "bf16_fold"):
+    the GEMM reads the un-normalised rows and the gamma-scaled weights as bf16 and the row statistics are applied to the
+    product,  rstd * (bf16(h) bf16(gamma*W)^T - mean * c) + (b + W beta)  with c = row sums of the rounded weights and
+    one-pass fp32 statistics.  Algebraically identical to LayerNorm followed by Linear (modeling_clip.py CLIPEncoderLayer)."""
+    E = h.shape[-1]
+    mean = h.sum(-1, keepdim=True) / E
+    var = ((h * h).sum(-1, keepdim=True) / E - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + eps)
+    w_f = _r(W * gamma.unsqueeze(0), "bf16")
+    c = w_f.double().sum(-1).float()
+    b_f = (b.double() + W.double() @ beta.double()).float()
+    return rstd * (_r(h, "bf16") @ w_f.t() - mean * c) + b_f
 
 
 def quick_gelu(x: torch.Tensor) -> torch.Tensor:
@@ -66,19 +82,26 @@ def vit_hidden(pixels: torch.Tensor, sd: dict, n_layers_run: int, cfg: VitCfg = 
     x = torch.cat([cls, x], dim=1) + sd[p + "embeddings.position_embedding.weight"].unsqueeze(0)
     h = F.layer_norm(x, (E,), sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"], 1e-5)
     hs = [h]
+    fold = emulate == "bf16_fold"
     for l in range(n_layers_run):
         q_ = f"{p}encoder.layers.{l}."
-        y = _r(F.layer_norm(h, (E,), sd[q_ + "layer_norm1.weight"], sd[q_ + "layer_norm1.bias"], 1e-5), emulate)
+        g1, b1 = sd[q_ + "layer_norm1.weight"], sd[q_ + "layer_norm1.bias"]
+        y = None if fold else _r(F.layer_norm(h, (E,), g1, b1, 1e-5), emulate)
 
         def lin(t, nm):
             return t @ _r(sd[f"{q_}{nm}.weight"], emulate).t() + sd[f"{q_}{nm}.bias"]
 
-        S = y.shape[1]
-        qh = _r(lin(y, "self_attn.q_proj") * dh ** -0.5, emulate).reshape(N, S, H, dh).transpose(1, 2)
-        kh = _r(lin(y, "self_attn.k_proj"), emulate).reshape(N, S, H, dh).transpose(1, 2)
-        vh = _r(lin(y, "self_attn.v_proj"), emulate).reshape(N, S, H, dh).transpose(1, 2)
+        def ln_lin(t, y_, g, b, nm, scale=1.0):      # LayerNorm + Linear, in the regime's arithmetic
+            if fold:
+                return folded_layernorm_linear(t, g, b, sd[f"{q_}{nm}.weight"] * scale, sd[f"{q_}{nm}.bias"] * scale)
+            return lin(y_, nm) * scale
+
+        S = h.shape[1]
+        qh = _r(ln_lin(h, y, g1, b1, "self_attn.q_proj", dh ** -0.5), emulate).reshape(N, S, H, dh).transpose(1, 2)
+        kh = _r(ln_lin(h, y, g1, b1, "self_attn.k_proj"), emulate).reshape(N, S, H, dh).transpose(1, 2)
+        vh = _r(ln_lin(h, y, g1, b1, "self_attn.v_proj"), emulate).reshape(N, S, H, dh).transpose(1, 2)
         sc = qh @ kh.transpose(-1, -2)
-        if emulate == "bf16":
+        if emulate is not None:
             # the kernel normalises after the PV product: P~ = exp(s - max) in bf16, / rowsum(fp32)
             m = sc.max(-1, keepdim=True).values
             pe = torch.exp(sc - m)
@@ -87,8 +110,9 @@ def vit_hidden(pixels: torch.Tensor, sd: dict, n_layers_run: int, cfg: VitCfg = 
             a = torch.softmax(sc, dim=-1) @ vh
         a = _r(a.transpose(1, 2).reshape(N, S, E), emulate)
         h = h + lin(a, "self_attn.out_proj")
-        y = _r(F.layer_norm(h, (E,), sd[q_ + "layer_norm2.weight"], sd[q_ + "layer_norm2.bias"], 1e-5), emulate)
-        f = _r(quick_gelu(lin(y, "mlp.fc1")), emulate)
+        g2, b2 = sd[q_ + "layer_norm2.weight"], sd[q_ + "layer_norm2.bias"]
+        y = None if fold else _r(F.layer_norm(h, (E,), g2, b2, 1e-5), emulate)
+        f = _r(quick_gelu(ln_lin(h, y, g2, b2, "mlp.fc1")), emulate)
         h = h + lin(f, "mlp.fc2")
         hs.append(h)
     return hs if return_all else h

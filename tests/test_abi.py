@@ -57,11 +57,14 @@ def test_vit_layout_is_consistent(lib):
     for l in range(23):
         y = lay.layer[l]
         offs += [y.ln1_g, y.ln1_b, y.w_qkv, y.b_qkv, y.w_o, y.b_o, y.ln2_g, y.ln2_b, y.w_fc1, y.b_fc1, y.w_fc2, y.b_fc2]
+        f = lay.fold[l]                 # ABI 3: the folded-LayerNorm operands sit behind their layer
+        offs += [f.w_qkv_f, f.c_qkv, f.b_qkv_f, f.w_fc1_f, f.c_fc1, f.b_fc1_f]
     assert all(b > a for a, b in zip(offs, offs[1:])) and all(o % 256 == 0 for o in offs)
-    assert 570e6 < lay.total_bytes < 600e6
+    assert 900e6 < lay.total_bytes < 930e6   # 582 MB of ABI-2 operands + 23 x 14.7 MB of gamma-scaled QKV / fc1 weights
     lay24 = L.VitLayout()
     assert lib.hvlm_vit_l14_layout(24, C.byref(lay24)) == 0
     assert lay24.layer[5].w_fc1 == lay.layer[5].w_fc1          # prefix property: fewer layers can run from one blob
+    assert lay24.fold[22].w_fc1_f == lay.fold[22].w_fc1_f
     assert lib.hvlm_vit_l14_layout(25, C.byref(lay)) == L.lib().hvlm_vit_l14_layout(-1, C.byref(lay)) < 0
     assert lib.hvlm_vit_l14_workspace_bytes(100) > 400e6
 

@@ -627,14 +627,22 @@ def test_vit_l14_vs_hf_reference_fixture(golden, tower23, profile):
     assert isinstance(lst, list) and lst[0].shape == (1, 256, 1024) and lst[0].dtype == torch.float16
 
 
-def test_vit_l14_tracks_bf16_operand_oracle(tower23):
+@pytest.mark.parametrize("ln_fold", [1, 0])
+def test_vit_l14_tracks_bf16_operand_oracle(tower23, ln_fold):
     """Tight check against the oracle run with bf16-rounded GEMM operands (same numeric regime): catches
-    structural bugs that the 1e-2 fp32 tolerance could hide."""
+    structural bugs that the 1e-2 fp32 tolerance could hide.  Both LayerNorm schedules of the tower, each against the
+    oracle in ITS arithmetic: folded into the QKV / fc1 GEMMs (default; the GEMM reads bf16(x) and bf16(gamma*W)) and the
+    stand-alone LayerNorm kernels (the GEMM reads bf16(LN(x)) and bf16(W))."""
     tw, sd = tower23("strong")
     px = synth.pixels((1, 3, 224, 224), seed=5)
-    hid = tw.forward_hidden(px.to(DEV))
-    emu = restate.vit_hidden(px, sd, 23, emulate="bf16")
+    prev = ops.vit_set_ln_fold(ln_fold)
+    try:
+        hid = tw.forward_hidden(px.to(DEV))
+    finally:
+        ops.vit_set_ln_fold(prev)
+    emu = restate.vit_hidden(px, sd, 23, emulate="bf16_fold" if ln_fold else "bf16")
     assert relmax(hid, emu) <= 4e-3
+    assert relmax(hid, restate.vit_hidden(px, sd, 23)) <= TOL_BF16
 
 
 def test_tower_load_model_from_files(tower23, tmp_path):
