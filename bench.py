@@ -501,7 +501,10 @@ def run_forward(c, args, D, B, steps, warmup, full=True, static_splice=True):
         if getattr(arch, "_POOL_BEFORE_FC2", False):
             # two pooling launches per step: hidden f32 -> f32 and f1 bf16 [.,4096] -> bf16 (fc2 runs on the pooled rows)
             pool_bytes = B * (FRAMES * 256 * 1024 * 4 + 356 * 1024 * 4) + B * (FRAMES * 256 * 4096 * 2 + 356 * 4096 * 2)
-        bytes_ = {"layernorm": M * 1024 * (4 + 2), "pool": pool_bytes,
+        ln_fold = bool(ops.vit_set_ln_fold(-1))
+        # stand-alone LayerNorm launches: 4 B read + 2 B written per element; with the LayerNorms folded into the GEMMs the
+        # only launch left is the tower's pre_layrnorm (fp32 in place + the bf16 copy of the rows)
+        bytes_ = {"layernorm": M * 1024 * ((4 + 4 + 2) if ln_fold else (4 + 2)), "pool": pool_bytes,
                   "splice": B * ((T_PROMPT - 1 + 356) * D * 2 + (T_PROMPT + 355) * (D * 2 + 9))}
         stages = {}
         for k, (t, n) in prof.items():
@@ -518,11 +521,13 @@ def run_forward(c, args, D, B, steps, warmup, full=True, static_splice=True):
             stages[k] = st
         dom = "fc1_gemm"
         achieved = stages[dom]["tflops"]
-        res["roofline"] = {"kernel": "gemm2_tcgen05_kernel<EPI_GELU_BF16> (2-CTA tcgen05 GEMM, ViT fc1: M=%d N=4096 K=1024)" % M,
+        res["roofline"] = {"kernel": "gemm2_tcgen05_kernel<EPI_GELU_BF16%s> (2-CTA tcgen05 GEMM, ViT fc1: M=%d N=4096 K=1024)"
+                                     % (", LayerNorm folded in" if ln_fold else "", M),
                            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                            "frac": round(achieved / pk["tf_sustained"], 4),
                            "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
-                           "traffic": traffic_for("fc1_gemm", M)}
+                           "traffic": traffic_for("fc1_gemm" if ln_fold else "fc1_gemm_ln_fold_off", M)}
+        res["ln_fold"] = ln_fold
         gemm_keys = ("qkv_gemm", "outproj_gemm", "fc1_gemm", "fc2_gemm")
         gemm_ms = sum(stages[k]["ms_per_step"] for k in gemm_keys if k in stages)
         # FLOPs actually executed: per-stage launches (the last fc2 runs on the pooled rows only, counted under "gemm")

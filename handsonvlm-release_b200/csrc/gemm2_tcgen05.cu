@@ -11,6 +11,9 @@
 //   * every CTA runs the same 4-warp epilogue as the 1-CTA kernel on its own 128 x 256 half (TMEM -> registers ->
 //     bias / quick-GELU -> swizzled smem -> TMA store / TMA reduce-add), double-buffered against the next tile's MMAs;
 //     the peer's epilogue threads release the accumulator with remote mbarrier arrivals on the leader
+//   * LayerNorm folded into the GEMMs around it (template FOLD; the tower's default, see vit_forward.cu): the QKV / fc1
+//     epilogues apply the row's (mean, rstd) to products of the UN-normalised bf16 rows with gamma-scaled weights, and the
+//     residual GEMMs in front of them (residual-LOAD epilogue, template RL) emit those bf16 rows and the rows' statistics
 #include <cstdlib>
 
 #include "gemm_epilogue.cuh"
@@ -41,10 +44,10 @@ constexpr int BK = 64;
 constexpr int kThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue (+ warps 6..9: 2nd epilogue group)
 // G = number of 4-warp epilogue groups (each owns half of the tile's columns when G == 2)
 // RL = "residual load" epilogue: the fp32 residual tile is TMA-LOADED into the staging buffer, the accumulator is added
-//      in shared memory and the sum leaves with a plain TMA store (4 staging buffers: the load runs two units ahead)
+//      in shared memory and the sum leaves with a plain TMA store
 // RL = 0: off; 4: four staging buffers, the residual load runs two units ahead (short K: the epilogue is the critical path);
-//      2: two buffers, one unit ahead behind an L2 prefetch of the whole next tile, and the K pipeline keeps its six stages
-//         (long K: the epilogue has slack, the K loop does not -- 4 instead of 5 stages cost the K = 4096 GEMM 20 us)
+//      2: two buffers, one unit ahead, and the K pipeline keeps its six stages (long K: the epilogue has slack, the K loop
+//         does not -- 4 stages instead of 5 cost the K = 4096 GEMM 20 us per call, 5 instead of 6 cost 6 us)
 template <int G, int RL = 0>
 struct Cfg2 {
     static constexpr int kStages = (G == 2 || RL == 4) ? 5 : 6;

@@ -110,12 +110,6 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                  "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                  : "memory");
 }
-// warm the L2 with a tile that a later TMA load will fetch (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
-                 "r"(c0), "r"(c1)
-                 : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {   // <= N groups still reading their smem source

@@ -722,7 +722,9 @@ def test_bench_line_has_the_contract_keys(tmp_path):
         assert k in line, k
     assert line["unit"] == "frames/s" and line["n_gpus"] == 1 and line["steps"] == 3 and line["warmup"] >= 3
     assert line["value"] > 1000 and abs(line["value"] - 100 / (line["ms_per_step"] / 1e3)) / line["value"] < 1e-3
-    assert line["gpu_launches"] == 3 * 171
+    # per step: im2col + patch GEMM + pre-LayerNorm + 23 x (QKV, attention, out_proj, fc1, fc2) - the pooled last fc2
+    # + 2 pools + 2 GEMMs + 3 splice + gather = 125 (171 with HVLM_LN_FOLD=0: two LayerNorm launches more per layer)
+    assert line["gpu_launches"] == 3 * 125
     rf = line["roofline"]
     assert rf["bound"] == "tensor" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3 and 0.3 < rf["frac"] < 1.2
     e = line["e2e"]
