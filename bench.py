@@ -527,6 +527,10 @@ def run_forward(c, args, D, B, steps, warmup, full=True, static_splice=True):
                            "frac": round(achieved / pk["tf_sustained"], 4),
                            "peak_source": pk["src"] + ", sustained figure (kernel timed inside a long step)",
                            "traffic": traffic_for("fc1_gemm" if ln_fold else "fc1_gemm_ln_fold_off", M)}
+        if ln_fold:
+            res["roofline"]["note"] = ("achieved counts the GEMM's 2*M*N*K only; this launch also performs LayerNorm 2 of the "
+                                       "layer (folded into its epilogue: HVLM_LN_FOLD=0 runs the plain kernel at ~0.93 of the "
+                                       "same peak, and the whole step 2.8 % slower, profiles/r2_ab_ln_fold.txt)")
         res["ln_fold"] = ln_fold
         gemm_keys = ("qkv_gemm", "outproj_gemm", "fc1_gemm", "fc2_gemm")
         gemm_ms = sum(stages[k]["ms_per_step"] for k in gemm_keys if k in stages)

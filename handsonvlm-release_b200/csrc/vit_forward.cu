@@ -162,6 +162,11 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         return e && e[0] == '1';
     }();
     const bool fold = !fuse_ln && ln_fold_setting() != 0 && n_layers_run > 0;
+    // tile traversal directions of the four layer GEMMs (bit 0 QKV, 1 out_proj, 2 fc1, 3 fc2: 1 = last-to-first); A/B switch
+    static const int rev_mask = []() {
+        const char* e = getenv("HVLM_GEMM_REV_MASK");
+        return e ? atoi(e) : 8;
+    }();
     float* stats = reinterpret_cast<float*>(w8 + ws.stats);
     int32_t* ln_count = reinterpret_cast<int32_t*>(w8 + ws.ln_count);
     if (fuse_ln && cudaMemsetAsync(ln_count, 0, static_cast<size_t>((M + 127) / 128) * 4, s) != cudaSuccess) return HVLM_ERR_CUDA;
@@ -204,6 +209,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             EpiArgs ep;
             ep.bias = f32(fold ? yf.b_qkv_f : y.b_qkv);
             ep.out = w8 + ws.qkv;
+            ep.reverse = rev_mask & 1;
             if (fold) {      // LN1 folded in: A = bf16 residual rows, B = gamma-scaled weights
                 ep.ln_c = f32(yf.c_qkv);
                 ep.ln_stats = stats;
@@ -222,6 +228,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             ep.bias = f32(y.b_o);
             ep.resid = hidden;
             ep.out = hidden;
+            ep.reverse = (rev_mask >> 1) & 1;
             if (fuse_ln) {   // LN2 fused: y = LN2(hidden) is produced as row blocks complete
                 ep.ln_gamma = f32(y.ln2_g);
                 ep.ln_beta = f32(y.ln2_b);
@@ -245,6 +252,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             EpiArgs ep;
             ep.bias = f32(fold ? yf.b_fc1_f : y.b_fc1);
             ep.out = w8 + ws.f1;
+            ep.reverse = (rev_mask >> 2) & 1;
             if (fold) {
                 ep.ln_c = f32(yf.c_fc1);
                 ep.ln_stats = stats;
@@ -259,7 +267,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             ep.bias = f32(y.b_fc2);
             ep.resid = hidden;
             ep.out = hidden;
-            ep.reverse = 1;   // fc1 wrote f1 first-to-last: its tail is what L2 still holds
+            ep.reverse = (rev_mask >> 3) & 1;   // default 1: fc1 wrote f1 first-to-last, its tail is what L2 still holds
             if (fuse_ln && l + 1 < n_layers_run) {   // LN1 of the next layer fused into this GEMM
                 ep.ln_gamma = f32(L.layer[l + 1].ln1_g);
                 ep.ln_beta = f32(L.layer[l + 1].ln1_b);
