@@ -111,6 +111,30 @@ __device__ __forceinline__ void max_chunk32(const uint32_t (&v)[32], float& m) {
     }
     m = fmaxf(a, b);
 }
+// 2^x for a PAIR of arguments on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic for 2^f
+// (relative error 4e-4, far below the bf16 rounding of P), exponent inserted with an integer add.  x <= 0 here (row maximum
+// subtracted); arguments below -126 are clamped (their probabilities flush to zero either way).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+    constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: x + kMagic keeps round(x) in the low mantissa bits
+    x0 = fmaxf(x0, -126.0f);
+    x1 = fmaxf(x1, -126.0f);
+    float t0, t1, n0, n1, f0, f1;
+    fadd2(t0, t1, x0, x1, kMagic, kMagic);
+    fadd2(n0, n1, t0, t1, -kMagic, -kMagic);
+    fadd2(f0, f1, x0, x1, -n0, -n1);
+    float q0, q1;
+    ffma2(q0, q1, f0, f1, 0.0555041f, 0.0555041f, 0.2402265f, 0.2402265f);
+    ffma2(q0, q1, q0, q1, f0, f1, 0.6931472f, 0.6931472f);
+    ffma2(q0, q1, q0, q1, f0, f1, 1.0f, 1.0f);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+#ifndef HVLM_ATTN_POLY
+#define HVLM_ATTN_POLY 0      // exp pass: every HVLM_ATTN_POLY-th pair of probabilities takes exp2_poly2 instead of MUFU.EX2 (0: none)
+                              // measured stand-alone, 100 frames: 61.9 us (0) / 61.6 (4: 12.5 %) / 61.9 (2: 25 %) / 69.1 (1: 50 %): the
+                              // exp pass is not what bounds the kernel (its serial chain per tile is) -- off
+#endif
+
 // The softmax warps are issue-bound as much as MUFU-bound (two of them share a scheduler), so the exp pass and the
 // epilogue use the packed fp32x2 FMA / ADD / MUL of hvlm_ptx.cuh: fewer instructions per element is what pays.
 // p = 2^(s*log2e - mxl) for one 32-column chunk; packed bf16 pairs; returns the chunk's sum
@@ -122,7 +146,13 @@ __device__ __forceinline__ float exp_chunk32(const uint32_t (&v)[32], float log2
         float x0, x1, x2, x3;
         ffma2(x0, x1, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), log2e, log2e, nm, nm);
         ffma2(x2, x3, __uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3]), log2e, log2e, nm, nm);
-        const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+        float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2, p3;
+        if (HVLM_ATTN_POLY != 0 && ((j / 2) % HVLM_ATTN_POLY) == HVLM_ATTN_POLY - 1) {
+            exp2_poly2(x2, x3, p2, p3);
+        } else {
+            p2 = fast_exp2(x2);
+            p3 = fast_exp2(x3);
+        }
         fadd2(s0, s1, s0, s1, p0, p1);
         fadd2(t0, t1, t0, t1, p2, p3);
         pk[j] = pack_bf16(p0, p1);

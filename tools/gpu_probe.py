@@ -11,6 +11,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import hvlm_b200  # noqa: E402
+from hvlm_b200 import _lib as _L  # noqa: E402
+if os.environ.get("HVLM_PROBE_LIB"):          # a library variant built by tools/build_probe_libs.sh
+    _L.LIB_PATH = os.path.abspath(os.environ["HVLM_PROBE_LIB"])
 from hvlm_b200 import ops  # noqa: E402
 from oracle import restate, synth  # noqa: E402
 
