@@ -52,7 +52,7 @@ template <int G, int RL = 0>
 struct Cfg2 {
     static constexpr int kStages = (G == 2 || RL == 4) ? 5 : 6;
     static constexpr int kBufs = RL ? RL : 2;                    // staging buffers per epilogue group
-    static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * kBufs * (BM * 128) + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * (BM * BK * 2 + (BN / 2) * BK * 2) + G * kBufs * (BM * 128) + 1024 + 256 + 1024;   // + barriers + folded-epilogue vectors
 };
 constexpr int kABytes = BM * BK * 2;            // 16 KB
 constexpr int kBBytes = (BN / 2) * BK * 2;      // 16 KB (this CTA's half of B)
@@ -233,6 +233,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     uint64_t* ld_bar = bars + 2 * kStages + 5;       // [4]        RL only: residual tile landed in staging buffer i
     uint64_t* xfull_bar = ld_bar + 4;                // [4]        RL + FOLD: epilogue (128) -> copy warps: buffer i holds the sums
     uint64_t* xdone_bar = xfull_bar + 4;             // [4]        RL + FOLD: copy warps (128) -> store warp: buffer i was read
+    float4* smem_bc = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [G][32] FOLD consumer: folded bias |
+                                                                                           //   column sums of the current unit
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -408,6 +410,38 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             }
         };
         stats_fetch(pair);
+        // FOLD consumer: the unit's 64 folded-bias values and 64 column sums are staged in shared memory, fetched ONE UNIT
+        // AHEAD by the group's first 32 threads (16 bytes each) -- the warp-uniform loads they replace cost an L2 round trip
+        // per 32-column chunk on the epilogue's critical path
+        [[maybe_unused]] float4* bc_s = smem_bc + grp * 32;
+        [[maybe_unused]] float4 bc_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        [[maybe_unused]] int bc_v = pair, bc_uu = 0, bc_units = 0, bc_col0 = 0;
+        auto bc_tile = [&]() {
+            if (bc_v < sched.nv) {
+                int mb, nb, hf;
+                sched.decode(bc_v, mb, nb, hf);
+                bc_units = hf < 0 ? kUnits : kUnits / 2;
+                bc_col0 = nb * BN + (hf < 0 ? 0 : hf * (BN / 2)) + grp * bc_units * kUnitCols;
+            }
+        };
+        auto bc_fetch = [&]() {
+            if constexpr (FOLD && !RL) {
+                if (bc_v < sched.nv) {
+                    if (row < 32)
+                        bc_next = __ldg(reinterpret_cast<const float4*>((row < 16 ? ep.bias : ep.ln_c) + bc_col0 +
+                                                                        bc_uu * kUnitCols + 4 * (row & 15)));
+                    if (++bc_uu == bc_units) {
+                        bc_uu = 0;
+                        bc_v += n_pairs;
+                        bc_tile();
+                    }
+                }
+            }
+        };
+        if constexpr (FOLD && !RL) {
+            bc_tile();
+            bc_fetch();
+        }
         for (int v = pair; v < sched.nv; v += n_pairs) {
             int m_blk, n_blk, half;
             sched.decode(v, m_blk, n_blk, half);
@@ -449,6 +483,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         if (elect_one()) bulk_wait_read<1>();
                         __syncwarp();
                     }
+                    if constexpr (FOLD) {
+                        // (every thread of the group passed the previous unit's bar_b after its last read of bc_s)
+                        if (row < 32) bc_s[row] = bc_next;
+                        bc_fetch();
+                    }
                     named_bar_sync(bar_a, 128);
                 }
                 const int n0 = ncol0 + u * kUnitCols;
@@ -465,7 +504,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         else mbar_arrive_cluster(&tempty_bar[acc], 0);
                     }
                     float v[32];
-                    if constexpr (FOLD && !RL) epilogue_math_fold<EPI>(r, ep.bias, ep.ln_c, n0 + h * 32, f_rstd, f_nmr, v);
+                    if constexpr (FOLD && !RL) epilogue_math_fold<EPI>(r, bc_s + h * 8, bc_s + 16 + h * 8, f_rstd, f_nmr, v);
                     else epilogue_math<EPI>(r, ep.bias, n0 + h * 32, v);
                     if constexpr (RL) {
                         mbar_wait(&ld_bar[ucount & static_cast<uint32_t>(kBufs - 1)], (ucount / static_cast<uint32_t>(kBufs)) & 1u);

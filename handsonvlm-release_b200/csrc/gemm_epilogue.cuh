@@ -47,16 +47,16 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], const f
 }
 
 // LayerNorm folded into the GEMM (see EpiArgs::ln_stats): v = rstd * acc + (bias[n] - mean * rstd * c[n]) -> (quick-GELU)
+// b4 / c4: the 32 columns' folded bias and column sums, staged in SHARED memory by the caller (every thread of the group reads
+// the same addresses: broadcast).  From global memory these warp-uniform loads cost an L2 round trip per 32-column chunk --
+// a pair meets each column block only once or twice per launch -- which ncu showed as a quarter of the epilogue's time.
 template <int EPI>
-__device__ __forceinline__ void epilogue_math_fold(const uint32_t (&acc)[32], const float* __restrict__ bias,
-                                                   const float* __restrict__ csum, int n0, float rstd, float nmr,
-                                                   float (&v)[32]) {
-    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
-    const float4* c4 = reinterpret_cast<const float4*>(csum + n0);
+__device__ __forceinline__ void epilogue_math_fold(const uint32_t (&acc)[32], const float4* b4, const float4* c4, float rstd,
+                                                   float nmr, float (&v)[32]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        const float4 c = __ldg(c4 + j);
+        const float4 b = b4[j];
+        const float4 c = c4[j];
         // packed fp32x2 FMAs: the epilogue warps are alone on their schedulers, instruction count is what they pay for
         float t0, t1, t2, t3;
         ffma2(t0, t1, nmr, nmr, c.x, c.y, b.x, b.y);
