@@ -16,7 +16,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "gemm_epilogue.cuh"
 #include "hvlm_internal.cuh"
@@ -39,10 +41,55 @@ static void load_encode() {
     }
 }
 
+// Descriptor cache.  A forward of the tower encodes ~4 tensor maps for each of its ~95 GEMM / attention launches, and the
+// same (pointer, shape, box) tuples come back every step (weights never move, the caching allocator hands the workspace and
+// the residual stream out at the same addresses): a CUtensorMap is a pure function of its arguments (it holds an address,
+// not a reference), so the encoded 128 bytes are memoised.  HVLM_TMAP_CACHE=0 disables it (A/B runs).
+struct TmapKey {
+    uint64_t base, dims[5], str[4];
+    uint32_t box[5], rank, dt, swz;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 0x100000001b3ull;
+        return static_cast<size_t>(h ^ (h >> 29));
+    }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "hashed as 64-bit words");
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 8192;      // ~2 MB of host memory; cleared wholesale when full
+
 static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     std::call_once(g_encode_once, load_encode);
     if (!g_encode) return HVLM_ERR_CUDA;
+    static const bool use_cache = []() {
+        const char* e = getenv("HVLM_TMAP_CACHE");
+        return !(e && e[0] == '0');
+    }();
+    TmapKey key;
+    if (use_cache) {
+        memset(&key, 0, sizeof(key));
+        key.base = reinterpret_cast<uint64_t>(base);
+        key.rank = static_cast<uint32_t>(rank);
+        key.dt = static_cast<uint32_t>(dt);
+        key.swz = static_cast<uint32_t>(swz);
+        for (int i = 0; i < rank; ++i) {
+            key.dims[i] = dims[i];
+            key.box[i] = box[i];
+            if (i > 0) key.str[i - 1] = strides_bytes[i - 1];
+        }
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        auto it = g_tmap_cache.find(key);
+        if (it != g_tmap_cache.end()) {
+            *out = it->second;
+            return HVLM_OK;
+        }
+    }
     cuuint64_t gdim[5];
     cuuint64_t gstr[5];
     cuuint32_t bx[5];
@@ -59,6 +106,11 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS && getenv("HVLM_DEBUG"))
         fprintf(stderr, "[hvlm] cuTensorMapEncodeTiled failed: CUresult %d (rank %d)\n", static_cast<int>(r), rank);
+    if (r == CUDA_SUCCESS && use_cache) {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+        g_tmap_cache.emplace(key, *out);
+    }
     return r == CUDA_SUCCESS ? HVLM_OK : HVLM_ERR_CUDA;
 }
 
