@@ -63,9 +63,9 @@ SIGNATURES = {
     "hvlm_vit_l14_fwd_open_mlp": (i32, [p, i32, p, i32, p, p, i32, p, p, sz, C.POINTER(C.c_uint64), p]),
     "hvlm_feature_select": (i32, [p, p, i32, i32, i32, p]),
     "hvlm_layernorm_1024": (i32, [p, p, p, p, i32, i32, f32, p]),
-    "hvlm_layernorm_1024_stats": (i32, [p, p, p, p, p, p, i32, f32, p]),
-    "hvlm_gemm_ln_fold_bf16": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, f32, p]),
-    "hvlm_gemm_resid_stats": (i32, [p, p, p, p, p, p, i32, i32, p]),
+    "hvlm_layernorm_1024_stats": (i32, [p, p, p, p, p, p, p, i32, f32, p]),
+    "hvlm_gemm_ln_fold_bf16": (i32, [p, p, p, p, p, p, i32, i32, i32, i32, f32, p, p]),
+    "hvlm_gemm_resid_stats": (i32, [p, p, p, p, p, p, p, i32, i32, p]),
     "hvlm_vit_set_ln_fold": (i32, [i32]),
     "hvlm_vit_qkv_gemm": (i32, [p, p, p, p, i32, p]),
     "hvlm_vit_attention": (i32, [p, p, i32, p]),

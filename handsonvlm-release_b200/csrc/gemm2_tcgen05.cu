@@ -410,6 +410,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             }
         };
         stats_fetch(pair);
+        // FOLD producer: the row's centre (EpiArgs::shift_in), fetched one tile ahead like the statistics
+        [[maybe_unused]] float sh_next = 0.f;
+        auto shift_fetch = [&](int v) {
+            if constexpr (kXb) {
+                int m_blk = 0, n_blk, half;
+                if (v < sched.nv) sched.decode(v, m_blk, n_blk, half);
+                const int grow = m_blk * 2 * BM + static_cast<int>(rank) * BM + row;
+                sh_next = (ep.shift_in != nullptr && grow < M) ? __ldcg(ep.shift_in + grow) : 0.f;
+            }
+        };
+        shift_fetch(pair);
         // FOLD consumer: the unit's 64 folded-bias values and 64 column sums are staged in shared memory, fetched ONE UNIT
         // AHEAD by the group's first 32 threads (16 bytes each) -- the warp-uniform loads they replace cost an L2 round trip
         // per 32-column chunk on the epilogue's critical path
@@ -453,8 +464,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
             [[maybe_unused]] float f_rstd = 1.f, f_nmr = 0.f;      // consumer: this thread's row statistics
             [[maybe_unused]] float f_s = 0.f, f_ss = 0.f;          // producer: running (sum, sum of squares) of 128 columns
             if constexpr (FOLD && !RL) {
-                fold_row_stats(st_next, ep.ln_eps, f_rstd, f_nmr);
+                float f_mean;
+                fold_row_stats(st_next, ep.ln_eps, f_rstd, f_nmr, f_mean);
                 stats_fetch(v + n_pairs);
+                // the row's running mean for the next producer: one writer per row (first column tile, first half, first group)
+                if (ep.shift_io != nullptr && n_blk == 0 && half <= 0 && grp == 0 && m0 + row < M)
+                    ep.shift_io[m0 + row] += f_mean;
+            }
+            [[maybe_unused]] float f_shift = 0.f;                  // producer: this thread's row centre
+            if constexpr (kXb) {
+                f_shift = sh_next;
+                shift_fetch(v + n_pairs);
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -518,8 +538,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                             x.w += v[4 * j + 3];
                             *p4 = x;
                             if constexpr (FOLD) {
-                                f_s += (x.x + x.y) + (x.z + x.w);
-                                f_ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, f_ss))));
+                                const float d0 = x.x - f_shift, d1 = x.y - f_shift, d2 = x.z - f_shift, d3 = x.w - f_shift;
+                                f_s += (d0 + d1) + (d2 + d3);
+                                f_ss = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, f_ss))));
                             }
                         }
                         if constexpr (FOLD) {
@@ -626,6 +647,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                 const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
                 const int units = half < 0 ? kUnits : kUnits / 2;
                 const int ncol0 = n_blk * BN + (half < 0 ? 0 : half * (BN / 2));
+                float sh[8];            // the centres of this lane's eight rows of the tile
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int grow = m0 + cw * 32 + 4 * i + (lane >> 3);
+                    sh[i] = (ep.shift_in != nullptr && grow < M) ? __ldcg(ep.shift_in + grow) : 0.f;
+                }
 #pragma unroll 1
                 for (int uu = 0; uu < units; ++uu, ++ucount) {
                     const uint32_t b = ucount & static_cast<uint32_t>(kBufs - 1);
@@ -644,7 +671,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
                         const int rr = cw * 32 + 4 * i + (lane >> 3);
                         if (m0 + rr < M)
                             *reinterpret_cast<uint2*>(xo + static_cast<size_t>(m0 + rr) * N) =
-                                make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
+                                make_uint2(pack_bf16(x[i].x - sh[i], x[i].y - sh[i]), pack_bf16(x[i].z - sh[i], x[i].w - sh[i]));
                     }
                 }
             }

@@ -70,8 +70,8 @@ __device__ __forceinline__ void epilogue_math_fold(const uint32_t (&acc)[32], co
     }
 }
 
-// (mean, rstd) of a 1024-wide row from its eight (sum, sum of squares) partials; returns rstd and nmr = -mean * rstd
-__device__ __forceinline__ void fold_row_stats(const float4 (&st)[4], float eps, float& rstd, float& nmr) {
+// (mean, rstd) of a 1024-wide row from its eight (sum, sum of squares) partials; returns rstd, nmr = -mean * rstd and mean
+__device__ __forceinline__ void fold_row_stats(const float4 (&st)[4], float eps, float& rstd, float& nmr, float& mean_out) {
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -82,6 +82,7 @@ __device__ __forceinline__ void fold_row_stats(const float4 (&st)[4], float eps,
     const float var = fmaxf(fmaf(-mean, mean, ss * (1.0f / 1024.0f)), 0.f);
     rstd = rsqrtf(var + eps);
     nmr = -mean * rstd;
+    mean_out = mean;
 }
 
 }  // namespace hvlm

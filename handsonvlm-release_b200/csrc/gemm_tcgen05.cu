@@ -590,7 +590,8 @@ extern "C" int hvlm_gemm_bf16(const void* A, const void* B, const float* bias, c
 }
 
 extern "C" int hvlm_gemm_ln_fold_bf16(const void* xb, const float* stats, const void* w_f, const float* c, const float* b_f,
-                                      void* out, int M, int N, int epilogue, int qkv_hm, float eps, void* stream) {
+                                      void* out, int M, int N, int epilogue, int qkv_hm, float eps, float* shift_io,
+                                      void* stream) {
     using namespace hvlm;
     if (!xb || !stats || !w_f || !c || !b_f || !out || M <= 0 || N <= 0) return HVLM_ERR_BAD_ARG;
     if (!aligned16(out) || !aligned16(stats) || !aligned16(c) || !aligned16(b_f)) return HVLM_ERR_ALIGN;
@@ -604,13 +605,14 @@ extern "C" int hvlm_gemm_ln_fold_bf16(const void* xb, const float* stats, const 
     ep.ln_c = c;
     ep.ln_stats = stats;
     ep.ln_eps = eps;
+    ep.shift_io = shift_io;
     ep.out = out;
     StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
     return launch_gemm(epi, xb, w_f, M, N, 1024, ep, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, void* xb_out,
-                                     float* stats_out, int M, int K, void* stream) {
+extern "C" int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, const float* shift,
+                                     void* xb_out, float* stats_out, int M, int K, void* stream) {
     using namespace hvlm;
     if (!hidden || !xb_out || !stats_out) return HVLM_ERR_BAD_ARG;
     if (!aligned16(hidden) || !aligned16(xb_out) || !aligned16(stats_out) || (bias && !aligned16(bias))) return HVLM_ERR_ALIGN;
@@ -620,6 +622,7 @@ extern "C" int hvlm_gemm_resid_stats(const void* A, const void* B, const float* 
     ep.out = hidden;
     ep.xb_out = xb_out;
     ep.stats_out = stats_out;
+    ep.shift_in = shift;
     StageTimer st(HVLM_STAGE_GEMM, static_cast<cudaStream_t>(stream));
     return launch_gemm(EPI_RESID_F32, A, B, M, 1024, K, ep, static_cast<cudaStream_t>(stream));
 }

@@ -45,6 +45,13 @@ struct EpiArgs {
     // the bf16 copy of the updated rows and their per-128-column statistics for the next folded GEMM
     void* xb_out = nullptr;            // bf16 [M,1024]
     float* stats_out = nullptr;        // f32 [M][8][2]
+    // Row centring.  LayerNorm does not see a constant added to a row, so the producer may subtract ANY per-row value before
+    // it rounds the row to bf16 and accumulates its statistics: xb = bf16(x - shift_i), stats over (x - shift_i), and the
+    // consumer's formula is unchanged.  With shift_i ~ the row mean the bf16 rounding acts on the centred row (as in
+    // LayerNorm-then-round) and the one-pass variance has nothing to cancel.  The consumer's n_blk == 0 tiles keep the
+    // running mean up to date for the next producer: shift_io[i] += mean of the centred row.
+    const float* shift_in = nullptr;   // producer: f32 [M] or null (= 0)
+    float* shift_io = nullptr;         // consumer: f32 [M] or null
 };
 
 // C = A[M,K] * B[N,K]^T with the chosen epilogue.  Returns an hvlm_status.

@@ -16,7 +16,7 @@
 namespace hvlm {
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
                      cudaStream_t s, int reverse, const float* add_rows = nullptr, int add_period = 1, void* xb_out = nullptr,
-                     float* stats_out = nullptr);
+                     float* stats_out = nullptr, float* shift_out = nullptr);
 int launch_im2col(const void* pixels, int pix_dtype, int n_frames, void* A, const float* cls, const float* pos,
                   float* x0, cudaStream_t s);
 int launch_im2col_u8(const uint8_t* frames, const float* mean, const float* stdv, int n_frames, void* A, const float* cls,
@@ -26,7 +26,7 @@ int launch_attention(const void* qkv, void* out, int n_frames, cudaStream_t s);
 static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 struct VitWorkspace {
-    uint64_t a_patch, y, qkv, attn, f1, ln_count, stats, total;
+    uint64_t a_patch, y, qkv, attn, f1, ln_count, stats, shift, total;
 };
 
 static VitWorkspace vit_workspace(int n_frames) {
@@ -46,6 +46,7 @@ static VitWorkspace vit_workspace(int n_frames) {
     w.f1 = take(M * 4096 * 2);
     w.ln_count = take(((M + 127) / 128) * 4);
     w.stats = take(M * 16 * 4);      // folded LayerNorm: (sum, sum of squares) per row and 128-column block
+    w.shift = take(M * 4);           // folded LayerNorm: the row's running mean (the centre of its bf16 copy / statistics)
     w.total = off;
     return w;
 }
@@ -168,6 +169,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         return e ? atoi(e) : 8;
     }();
     float* stats = reinterpret_cast<float*>(w8 + ws.stats);
+    float* shift = reinterpret_cast<float*>(w8 + ws.shift);
     int32_t* ln_count = reinterpret_cast<int32_t*>(w8 + ws.ln_count);
     if (fuse_ln && cudaMemsetAsync(ln_count, 0, static_cast<size_t>((M + 127) / 128) * 4, s) != cudaSuccess) return HVLM_ERR_CUDA;
 
@@ -193,7 +195,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         // + position embedding (tokens 1..256; the CLS row got pos[0] from im2col), then pre_layrnorm, in place
         // (folded LayerNorms: it also writes the bf16 rows + row statistics the first QKV GEMM consumes)
         rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1, f32(L.pos),
-                              HVLM_VIT_TOKENS, fold ? w8 + ws.y : nullptr, fold ? stats : nullptr);
+                              HVLM_VIT_TOKENS, fold ? w8 + ws.y : nullptr, fold ? stats : nullptr, fold ? shift : nullptr);
     }
     if (rc) return rc;
 
@@ -213,6 +215,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             if (fold) {      // LN1 folded in: A = bf16 residual rows, B = gamma-scaled weights
                 ep.ln_c = f32(yf.c_qkv);
                 ep.ln_stats = stats;
+                ep.shift_io = shift;
             }
             StageTimer st(HVLM_STAGE_QKV_GEMM, s);
             rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + (fold ? yf.w_qkv_f : y.w_qkv), M, 3072, 1024, ep, s);
@@ -238,6 +241,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             if (fold) {      // feeds the folded LN2 of fc1
                 ep.xb_out = w8 + ws.y;
                 ep.stats_out = stats;
+                ep.shift_in = shift;
             }
             StageTimer st(HVLM_STAGE_OUTPROJ_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.attn, wb + y.w_o, M, 1024, 1024, ep, s);
@@ -256,6 +260,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             if (fold) {
                 ep.ln_c = f32(yf.c_fc1);
                 ep.ln_stats = stats;
+                ep.shift_io = shift;
             }
             StageTimer st(HVLM_STAGE_FC1_GEMM, s);
             rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + (fold ? yf.w_fc1_f : y.w_fc1), M, 4096, 1024, ep, s);
@@ -277,6 +282,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             if (fold && l + 1 < n_layers_run) {      // feeds the folded LN1 of the next layer (nobody reads them after the last)
                 ep.xb_out = w8 + ws.y;
                 ep.stats_out = stats;
+                ep.shift_in = shift;
             }
             StageTimer st(HVLM_STAGE_FC2_GEMM, s);
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.f1, wb + y.w_fc2, M, 1024, 4096, ep, s);

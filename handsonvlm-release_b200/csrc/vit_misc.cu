@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
                                                             int rows, float eps, int reverse,
                                                             const float* __restrict__ add_rows, int add_period,
                                                             __nv_bfloat16* __restrict__ xb_out,
-                                                            float* __restrict__ stats_out) {
+                                                            float* __restrict__ stats_out, float* __restrict__ shift_out) {
     // the dependent launch is triggered at the END of this kernel: its successor is a GEMM whose CTAs would otherwise become
     // resident next to the LayerNorm CTAs right away (no shared memory to wait for) and halve their occupancy
     pdl_wait();
@@ -67,7 +67,23 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
     const float rstd = rsqrtf(sq * (1.0f / 1024.0f) + eps);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
-    [[maybe_unused]] float ys = 0.f, yss = 0.f;   // (sum, sum of squares) of the OUTPUT row (folded-LayerNorm feed)
+    [[maybe_unused]] float ys = 0.f, yss = 0.f;   // (sum, sum of squares) of the centred OUTPUT row (folded-LayerNorm feed)
+    [[maybe_unused]] float ymean = 0.f;           // the output row's mean = the centre the bf16 copy and the statistics use
+    if constexpr (sizeof(TOut) == 4) {
+        if (xb_out != nullptr) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = __ldg(g4 + lane + 32 * j);
+                const float4 b = __ldg(b4 + lane + 32 * j);
+                t += ((v[j].x - mean) * rstd * g.x + b.x) + ((v[j].y - mean) * rstd * g.y + b.y) +
+                     ((v[j].z - mean) * rstd * g.z + b.z) + ((v[j].w - mean) * rstd * g.w + b.w);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            ymean = t * (1.0f / 1024.0f);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 g = __ldg(g4 + lane + 32 * j);
@@ -81,12 +97,13 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
         if constexpr (sizeof(TOut) == 4) {
             *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
             if (xb_out != nullptr) {
-                // the tower's pre-LayerNorm feeds a GEMM with the next LayerNorm folded in: bf16 copy of the row + its
+                // the tower's pre-LayerNorm feeds a GEMM with the next LayerNorm folded in: bf16 copy of the CENTRED row + its
                 // statistics in the same [8][2] layout the residual GEMMs write (block 0 carries the whole row)
-                ys += (y[0] + y[1]) + (y[2] + y[3]);
-                yss = fmaf(y[0], y[0], fmaf(y[1], y[1], fmaf(y[2], y[2], fmaf(y[3], y[3], yss))));
-                __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]);
-                __nv_bfloat162 hi = __floats2bfloat162_rn(y[2], y[3]);
+                const float d0 = y[0] - ymean, d1 = y[1] - ymean, d2 = y[2] - ymean, d3 = y[3] - ymean;
+                ys += (d0 + d1) + (d2 + d3);
+                yss = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, yss))));
+                __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(d2, d3);
                 uint2 w;
                 w.x = *reinterpret_cast<uint32_t*>(&lo);
                 w.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -111,21 +128,24 @@ __global__ void __launch_bounds__(256) layernorm1024_kernel(const float* __restr
             if (lane < 8)
                 *reinterpret_cast<float2*>(stats_out + static_cast<size_t>(row) * 16 + lane * 2) =
                     lane == 0 ? make_float2(ys, yss) : make_float2(0.f, 0.f);
+            if (lane == 0 && shift_out != nullptr) shift_out[row] = ymean;
         }
     }
     pdl_launch_dependents();
 }
 
 int launch_layernorm(const float* x, const float* g, const float* b, void* out, int rows, int out_dtype, float eps,
-                     cudaStream_t s, int reverse, const float* add_rows, int add_period, void* xb_out, float* stats_out) {
+                     cudaStream_t s, int reverse, const float* add_rows, int add_period, void* xb_out, float* stats_out,
+                     float* shift_out) {
     const int grid = (rows + 7) / 8;
     if ((xb_out != nullptr) != (stats_out != nullptr) || (xb_out != nullptr && out_dtype != HVLM_F32)) return HVLM_ERR_BAD_ARG;
     if (out_dtype == HVLM_F32)
         launch_pdl_cls(0, layernorm1024_kernel<float>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<float*>(out), rows, eps, reverse, add_rows,
-                   add_period, static_cast<__nv_bfloat16*>(xb_out), stats_out);
+                   add_period, static_cast<__nv_bfloat16*>(xb_out), stats_out, shift_out);
     else if (out_dtype == HVLM_BF16)
         launch_pdl_cls(0, layernorm1024_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, x, g, b, static_cast<__nv_bfloat16*>(out), rows, eps,
-                   reverse, add_rows, add_period, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr));
+                   reverse, add_rows, add_period, static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr),
+                   static_cast<float*>(nullptr));
     else
         return HVLM_ERR_BAD_DTYPE;
     return check_last("layernorm");
@@ -338,17 +358,17 @@ extern "C" int hvlm_layernorm_1024(const float* x, const float* gamma, const flo
     if (!x || !gamma || !beta || !out || rows <= 0) return HVLM_ERR_BAD_ARG;
     if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(out)) return HVLM_ERR_ALIGN;
     return launch_layernorm(x, gamma, beta, out, rows, out_dtype, eps, static_cast<cudaStream_t>(stream), 0, nullptr, 1,
-                            nullptr, nullptr);
+                            nullptr, nullptr, nullptr);
 }
 
 extern "C" int hvlm_layernorm_1024_stats(const float* x, const float* gamma, const float* beta, float* out, void* xb_out,
-                                         float* stats_out, int rows, float eps, void* stream) {
+                                         float* stats_out, float* shift_out, int rows, float eps, void* stream) {
     using namespace hvlm;
-    if (!x || !gamma || !beta || !out || !xb_out || !stats_out || rows <= 0) return HVLM_ERR_BAD_ARG;
+    if (!x || !gamma || !beta || !out || !xb_out || !stats_out || !shift_out || rows <= 0) return HVLM_ERR_BAD_ARG;
     if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(out) || !aligned16(xb_out) || !aligned16(stats_out))
         return HVLM_ERR_ALIGN;
     return launch_layernorm(x, gamma, beta, out, rows, HVLM_F32, eps, static_cast<cudaStream_t>(stream), 0, nullptr, 1, xb_out,
-                            stats_out);
+                            stats_out, shift_out);
 }
 
 extern "C" int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls,

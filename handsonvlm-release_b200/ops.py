@@ -298,7 +298,8 @@ def layernorm_1024(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, out_dtype=
 
 
 def layernorm_1024_stats(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps=1e-5):
-    """LayerNorm with fp32 output plus what a folded GEMM consumes next: (out f32, bf16(out), stats f32 [rows,8,2])."""
+    """LayerNorm with fp32 output plus what a folded GEMM consumes next:
+    (out f32, bf16(out - shift), stats f32 [rows,8,2] of (out - shift), shift f32 [rows] = row mean of out)."""
     _need_cuda(x, g, b)
     ensure_device()
     x = x.contiguous()
@@ -306,15 +307,18 @@ def layernorm_1024_stats(x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, eps=
     out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
     xb = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     stats = torch.empty(rows, 8, 2, dtype=torch.float32, device=x.device)
-    L.check(L.lib().hvlm_layernorm_1024_stats(_p(x), _p(g), _p(b), _p(out), _p(xb), _p(stats), rows, eps, _stream()),
+    shift = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.check(L.lib().hvlm_layernorm_1024_stats(_p(x), _p(g), _p(b), _p(out), _p(xb), _p(stats), _p(shift), rows, eps, _stream()),
             "hvlm_layernorm_1024_stats")
-    return out, xb, stats
+    return out, xb, stats, shift
 
 
 def gemm_ln_fold(xb: torch.Tensor, stats: torch.Tensor, w_f: torch.Tensor, c: torch.Tensor, b_f: torch.Tensor, *,
-                 epilogue: str = "bias", qkv_hm: bool = False, eps: float = 1e-5) -> torch.Tensor:
-    """LayerNorm folded into its consumer GEMM (hvlm_gemm_ln_fold_bf16): xb bf16 [M,1024] un-normalised rows, stats
-    [M,8,2], w_f bf16 [N,1024] = gamma*W, c [N] its row sums, b_f [N] = b + W beta -> bf16 [M,N] (or [48,M,64])."""
+                 epilogue: str = "bias", qkv_hm: bool = False, eps: float = 1e-5,
+                 shift_io: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm folded into its consumer GEMM (hvlm_gemm_ln_fold_bf16): xb bf16 [M,1024] un-normalised (centred) rows, stats
+    [M,8,2], w_f bf16 [N,1024] = gamma*W, c [N] its row sums, b_f [N] = b + W beta -> bf16 [M,N] (or [48,M,64]).
+    ``shift_io`` f32 [M] (optional, updated IN PLACE): += the mean of each row of xb (the next producer's centre)."""
     _need_cuda(xb, stats, w_f, c, b_f)
     ensure_device()
     M, N = xb.shape[0], w_f.shape[0]
@@ -323,12 +327,14 @@ def gemm_ln_fold(xb: torch.Tensor, stats: torch.Tensor, w_f: torch.Tensor, c: to
     out = torch.empty((48, M, 64) if qkv_hm else (M, N), dtype=torch.bfloat16, device=xb.device)
     L.check(L.lib().hvlm_gemm_ln_fold_bf16(_p(xb.contiguous()), _p(stats), _p(w_f.contiguous()), _p(c), _p(b_f), _p(out), M, N,
                                            {"bias": L.EPI_BIAS, "quick_gelu": L.EPI_BIAS_QUICKGELU}[epilogue], int(qkv_hm), eps,
-                                           _stream()), "hvlm_gemm_ln_fold_bf16")
+                                           _p(shift_io), _stream()), "hvlm_gemm_ln_fold_bf16")
     return out
 
 
-def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], hidden: torch.Tensor):
-    """hidden f32 [M,1024] += a w^T + bias IN PLACE; returns (bf16(hidden), stats [M,8,2]) from the same epilogue."""
+def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], hidden: torch.Tensor,
+                     shift: Optional[torch.Tensor] = None):
+    """hidden f32 [M,1024] += a w^T + bias IN PLACE; returns (bf16(hidden - shift), stats [M,8,2] of (hidden - shift)) from
+    the same epilogue (shift f32 [M], default 0)."""
     _need_cuda(a, w, hidden)
     ensure_device()
     M, K = a.shape
@@ -336,8 +342,8 @@ def gemm_resid_stats(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and tuple(w.shape) == (1024, K)
     xb = torch.empty(M, 1024, dtype=torch.bfloat16, device=a.device)
     stats = torch.empty(M, 8, 2, dtype=torch.float32, device=a.device)
-    L.check(L.lib().hvlm_gemm_resid_stats(_p(a.contiguous()), _p(w.contiguous()), _p(bias), _p(hidden), _p(xb), _p(stats), M, K,
-                                          _stream()), "hvlm_gemm_resid_stats")
+    L.check(L.lib().hvlm_gemm_resid_stats(_p(a.contiguous()), _p(w.contiguous()), _p(bias), _p(hidden), _p(shift), _p(xb),
+                                          _p(stats), M, K, _stream()), "hvlm_gemm_resid_stats")
     return xb, stats
 
 

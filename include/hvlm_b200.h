@@ -175,24 +175,32 @@ HVLM_API int hvlm_vit_set_ln_fold(int on);
 /* building blocks of the tower, exported for per-stage parity tests */
 HVLM_API int hvlm_layernorm_1024(const float* x, const float* gamma, const float* beta, void* out, int rows, int out_dtype,
                         float eps, void* stream);
-/* The same LayerNorm with f32 output `out` [rows,1024] (may alias x) that also emits what a folded GEMM consumes next:
- * xb_out bf16 [rows,1024] = bf16(out) and stats_out f32 [rows][8][2] = (sum, sum of squares) of `out` per row
- * (block 0 carries the whole row, blocks 1..7 are zero).  This is the tower's pre_layrnorm. */
+/* The same LayerNorm with f32 output `out` [rows,1024] (may alias x) that also emits what a folded GEMM consumes next.
+ * A LayerNorm does not see a constant added to its row, so everything the fold hands over is CENTRED on a per-row value
+ * ("shift", ~ the row mean): the bf16 rounding then acts on the centred row, like LayerNorm-then-round does, and the
+ * one-pass variance has nothing to cancel.
+ *   shift_out f32 [rows]        = row mean of `out`
+ *   xb_out    bf16 [rows,1024]  = bf16(out - shift)
+ *   stats_out f32 [rows][8][2]  = (sum, sum of squares) of (out - shift) per row (block 0 carries the whole row, 1..7 zero)
+ * This is the tower's pre_layrnorm. */
 HVLM_API int hvlm_layernorm_1024_stats(const float* x, const float* gamma, const float* beta, float* out, void* xb_out,
-                                       float* stats_out, int rows, float eps, void* stream);
+                                       float* stats_out, float* shift_out, int rows, float eps, void* stream);
 /* LayerNorm folded into its consumer GEMM (replaces LayerNorm + Linear of HF CLIPEncoderLayer, modeling_clip.py, as run by
  * clip_encoder.py:39-51):   out[i,n] = act( rstd_i * (sum_k xb[i,k] w_f[n,k] - mean_i * c[n]) + b_f[n] )
- *   xb     bf16 [M,1024]  the un-normalised rows;  stats f32 [M][8][2] their (sum, sum of squares) per 128-column block
+ *   xb     bf16 [M,1024]  the un-normalised rows (minus any per-row constant: see hvlm_layernorm_1024_stats);
+ *   stats  f32 [M][8][2]  (sum, sum of squares) of those same rows per 128-column block
+ *   shift_io f32 [M] or NULL: the running row mean kept for the NEXT producer -- shift_io[i] += mean of row i of xb
  *   w_f, c, b_f           as described at hvlm_vit_layout.fold;  N % 256 == 0, K = 1024
  *   epilogue              HVLM_EPI_BIAS or HVLM_EPI_BIAS_QUICKGELU, bf16 output [M,N];  qkv_hm != 0 (N = 3072, bias
  *                         epilogue): column-block-major [48][M][64] output as hvlm_vit_qkv_gemm */
 HVLM_API int hvlm_gemm_ln_fold_bf16(const void* xb, const float* stats, const void* w_f, const float* c, const float* b_f,
-                                    void* out, int M, int N, int epilogue, int qkv_hm, float eps, void* stream);
+                                    void* out, int M, int N, int epilogue, int qkv_hm, float eps, float* shift_io,
+                                    void* stream);
 /* Residual GEMM that feeds a folded LayerNorm:  hidden[M,1024] (f32, in place) += A[M,K] B[1024,K]^T + bias, and the same
- * epilogue writes xb_out = bf16(hidden) and stats_out (layout above).  hidden equals what hvlm_gemm_bf16 with
- * HVLM_EPI_BIAS_RESIDUAL computes, bit for bit. */
-HVLM_API int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, void* xb_out,
-                                   float* stats_out, int M, int K, void* stream);
+ * epilogue writes xb_out = bf16(hidden - shift[i]) and stats_out over (hidden - shift[i]) (layout above; shift f32 [M] or
+ * NULL = 0).  hidden equals what hvlm_gemm_bf16 with HVLM_EPI_BIAS_RESIDUAL computes, bit for bit. */
+HVLM_API int hvlm_gemm_resid_stats(const void* A, const void* B, const float* bias, float* hidden, const float* shift,
+                                   void* xb_out, float* stats_out, int M, int K, void* stream);
 /* y bf16 [M = n_frames*257, 1024] (LN1 output) -> qkv bf16 COLUMN-BLOCK-MAJOR [48][M][64]: column blocks
  * q0..q15 | k0..k15 | v0..v15 of (y W_qkv^T + b); q carries the 64^-1/2 scale (folded into the packed weights).
  * Every (frame, head) operand is a contiguous [257][64] block. */

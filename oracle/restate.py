@@ -35,11 +35,15 @@ def _r(x: torch.Tensor, emulate: str | None) -> torch.Tensor:
 
 
 def folded_layernorm_linear(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, W: torch.Tensor, b: torch.Tensor,
-                            eps: float = 1e-5) -> torch.Tensor:
+                            eps: float = 1e-5, shift: torch.Tensor | None = None) -> torch.Tensor:
     """``LayerNorm(h) W^T + b`` in the arithmetic of the CUDA path's FOLDED LayerNorm (debug regime "bf16_fold"):
     the GEMM reads the un-normalised rows and the gamma-scaled weights as bf16 and the row statistics are applied to the
     product,  rstd * (bf16(h) bf16(gamma*W)^T - mean * c) + (b + W beta)  with c = row sums of the rounded weights and
-    one-pass fp32 statistics.  Algebraically identical to LayerNorm followed by Linear (modeling_clip.py CLIPEncoderLayer)."""
+    one-pass fp32 statistics.  Algebraically identical to LayerNorm followed by Linear (modeling_clip.py CLIPEncoderLayer).
+    ``shift`` [..., 1]: the per-row constant the producer subtracts before rounding / accumulating (LayerNorm does not see
+    it); the CUDA path uses the row's running mean."""
+    if shift is not None:
+        h = h - shift
     E = h.shape[-1]
     mean = h.sum(-1, keepdim=True) / E
     var = ((h * h).sum(-1, keepdim=True) / E - mean * mean).clamp_min(0.0)
@@ -83,6 +87,7 @@ def vit_hidden(pixels: torch.Tensor, sd: dict, n_layers_run: int, cfg: VitCfg = 
     h = F.layer_norm(x, (E,), sd[p + "pre_layrnorm.weight"], sd[p + "pre_layrnorm.bias"], 1e-5)
     hs = [h]
     fold = emulate == "bf16_fold"
+    shift = h.mean(-1, keepdim=True)      # "bf16_fold": the running row mean (pre_layrnorm writes the exact one)
     for l in range(n_layers_run):
         q_ = f"{p}encoder.layers.{l}."
         g1, b1 = sd[q_ + "layer_norm1.weight"], sd[q_ + "layer_norm1.bias"]
@@ -93,7 +98,8 @@ def vit_hidden(pixels: torch.Tensor, sd: dict, n_layers_run: int, cfg: VitCfg = 
 
         def ln_lin(t, y_, g, b, nm, scale=1.0):      # LayerNorm + Linear, in the regime's arithmetic
             if fold:
-                return folded_layernorm_linear(t, g, b, sd[f"{q_}{nm}.weight"] * scale, sd[f"{q_}{nm}.bias"] * scale)
+                return folded_layernorm_linear(t, g, b, sd[f"{q_}{nm}.weight"] * scale, sd[f"{q_}{nm}.bias"] * scale,
+                                               shift=shift)
             return lin(y_, nm) * scale
 
         S = h.shape[1]
@@ -109,10 +115,12 @@ def vit_hidden(pixels: torch.Tensor, sd: dict, n_layers_run: int, cfg: VitCfg = 
         else:
             a = torch.softmax(sc, dim=-1) @ vh
         a = _r(a.transpose(1, 2).reshape(N, S, E), emulate)
+        shift = shift + (h - shift).mean(-1, keepdim=True)        # the QKV GEMM's epilogue updates the running mean ...
         h = h + lin(a, "self_attn.out_proj")
         g2, b2 = sd[q_ + "layer_norm2.weight"], sd[q_ + "layer_norm2.bias"]
         y = None if fold else _r(F.layer_norm(h, (E,), g2, b2, 1e-5), emulate)
         f = _r(quick_gelu(ln_lin(h, y, g2, b2, "mlp.fc1")), emulate)
+        shift = shift + (h - shift).mean(-1, keepdim=True)        # ... and so does fc1's
         h = h + lin(f, "mlp.fc2")
         hs.append(h)
     return hs if return_all else h

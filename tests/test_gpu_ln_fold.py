@@ -36,13 +36,16 @@ def test_layernorm_with_stats(rows):
     x = synth.gen("lnf.x", (rows, 1024), 2.0, rows, mean=0.7).to(DEV)
     g = synth.gen("lnf.g", (1024,), 0.2, 1, mean=1.0).to(DEV)
     b = synth.gen("lnf.b", (1024,), 0.1, 2).to(DEV)
-    out, xb, stats = ops.layernorm_1024_stats(x, g, b)
+    out, xb, stats, shift = ops.layernorm_1024_stats(x, g, b)
     ref = F.layer_norm(x.cpu(), (1024,), g.cpu(), b.cpu(), 1e-5)
     assert relmax(out, ref) <= 1e-5
-    assert torch.equal(xb, out.to(torch.bfloat16))
-    want = block_stats(out).sum(1)                     # whole row
-    assert relmax(stats[:, 0], want) <= 1e-5
-    assert float(stats[:, 1:].abs().max()) == 0.0 if rows else True
+    assert relmax(shift, out.double().mean(-1).float()) <= 1e-5 or float(shift.abs().max()) < 1e-6     # the row mean of `out`
+    cen = out - shift[:, None]                                                    # what the fold hands over is centred
+    assert torch.equal(xb, cen.to(torch.bfloat16))
+    want = block_stats(cen).sum(1)                     # whole row
+    assert float((stats[:, 0, 1].cpu() - want[:, 1].cpu()).abs().max() / want[:, 1].abs().max()) <= 1e-5
+    assert float(stats[:, 0, 0].abs().max()) <= 2e-3 * float(out.abs().max())       # sum of the centred row ~ 0
+    assert float(stats[:, 1:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M,K", [(1, 1024), (300, 1024), (4099, 1024), (2570, 4096), (25700, 1024), (25700, 4096)])
@@ -66,6 +69,15 @@ def test_gemm_resid_stats(M, K):
     h2 = res.clone()
     xb2, stats2 = ops.gemm_resid_stats(a, w, bias, h2)
     assert torch.equal(h2, h) and torch.equal(xb2, xb) and torch.equal(stats2, stats)       # bit-reproducible
+    # with a per-row centre: same `hidden`, bf16 copy and statistics of the centred rows
+    shift = synth.gen("rs.s", (M,), 0.4, 5, mean=0.3).to(DEV)
+    h3 = res.clone()
+    xb3, stats3 = ops.gemm_resid_stats(a, w, bias, h3, shift=shift)
+    assert torch.equal(h3, h)
+    cen = h - shift[:, None]
+    assert torch.equal(xb3, cen.to(torch.bfloat16))
+    want3 = block_stats(cen)
+    assert float((stats3.cpu() - want3.cpu()).abs().max() / want3.abs().max()) <= 2e-6
 
 
 @pytest.mark.parametrize("M,N,epilogue,qkv_hm", [(1, 3072, "bias", True), (300, 3072, "bias", True), (2570, 3072, "bias", True),
@@ -102,6 +114,37 @@ def test_gemm_ln_fold(M, N, epilogue, qkv_hm):
     if qkv_hm:
         out1 = out1.permute(1, 0, 2).reshape(M, N)
     assert relmax(out1, out) <= 4e-3
+    # the running row mean kept for the next producer: only the tiles of the first column block write it, once per row
+    sh = synth.gen("gf.s", (M,), 1.0, 8).to(DEV)
+    sh0 = sh.clone()
+    ops.gemm_ln_fold(xb, stats, w_f.to(DEV), c.to(DEV), b_f.to(DEV), epilogue=epilogue, qkv_hm=qkv_hm, shift_io=sh)
+    assert relmax(sh - sh0, xc.double().mean(-1).float()) <= 1e-5
+
+
+@pytest.mark.parametrize("dc", [0.0, 50.0, -400.0])
+def test_fold_is_robust_to_a_row_offset(dc):
+    """What separates the fold from LayerNorm-then-round is a constant added to a row: rounding x to bf16 instead of x - mean
+    costs |mean| / std in relative precision, and the one-pass variance cancels.  The producers therefore centre the rows on
+    their running mean (any per-row constant is invisible to the LayerNorm): residual GEMM -> folded GEMM with a row offset
+    of `dc` standard deviations stays within the bf16 bar of the fp32 LayerNorm -> Linear."""
+    M, N = 600, 3072
+    res = synth.gen("dc.r", (M, 1024), 1.0, 3).to(DEV) + dc
+    a = synth.gen("dc.A", (M, 1024), 1.0, 3).to(torch.bfloat16).to(DEV)
+    w = synth.gen("dc.W", (1024, 1024), 0.5 * 1024 ** -0.5, 3).to(torch.bfloat16).to(DEV)
+    bias = synth.gen("dc.b", (1024,), 0.1, 3).to(DEV)
+    W = synth.gen("dc.W2", (N, 1024), 1024 ** -0.5, 5)
+    b = synth.gen("dc.b2", (N,), 0.3, 5)
+    g = synth.gen("dc.g", (1024,), 0.2, 5, mean=1.0)
+    beta = synth.gen("dc.beta", (1024,), 0.1, 6)
+    w_f, c, b_f = fold_layernorm(W, b, g, beta)
+    shift = res.mean(-1) + 0.3                       # "the previous mean": close to, not equal to, the new row mean
+    h = res.clone()
+    xb, stats = ops.gemm_resid_stats(a, w, bias, h, shift=shift)
+    sh = shift.clone()
+    out = ops.gemm_ln_fold(xb, stats, w_f.to(DEV), c.to(DEV), b_f.to(DEV), shift_io=sh)
+    plain = F.layer_norm(h.cpu(), (1024,), g, beta, 1e-5) @ W.t() + b
+    assert relmax(out, plain) <= 1e-2
+    assert relmax(sh, h.double().mean(-1).float()) <= 1e-4        # the running mean is the row mean again
 
 
 @pytest.fixture(scope="module")
