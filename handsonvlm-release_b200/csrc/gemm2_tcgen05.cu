@@ -199,11 +199,13 @@ struct Sched {
 };
 
 // FOLD = LayerNorm folded into the GEMMs around it (EpiArgs::ln_stats / xb_out):
-//   * consumer (RL == false; QKV / fc1): A holds the un-normalised bf16 rows, B the gamma-scaled weights; the epilogue
-//     applies the row's (mean, rstd), read once per tile from the eight per-128-column partial sums
-//   * producer (RL == true; out_proj / fc2): the residual-load epilogue holds the updated fp32 row values in registers, so
-//     it also writes their bf16 copy (the next GEMM's A operand) and the partial sums -- the LayerNorm kernel between the
-//     two GEMMs (4 KB read + 2 KB write per row) disappears
+//   * consumer (RL == 0; QKV / fc1): A holds the un-normalised bf16 rows, B the gamma-scaled weights; the epilogue applies
+//     the row's (mean, rstd), computed from the eight per-128-column partial sums (fetched one tile ahead), with the folded
+//     bias / column-sum vectors of the unit staged in shared memory; its first column tiles keep the rows' running mean
+//   * producer (RL != 0; out_proj / fc2): the residual-load epilogue holds the updated fp32 row values in registers, so it
+//     accumulates their partial sums (centred on the running mean), and four copy warps write the bf16 twin of every staged
+//     unit (the next GEMM's A operand) -- the LayerNorm kernel between the two GEMMs (4 KB read + 2 KB write per row)
+//     disappears
 template <int EPI, bool LN, int G, int RL, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads + ((LN || G == 2 || (RL != 0 && FOLD)) ? 128 : 0), 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
