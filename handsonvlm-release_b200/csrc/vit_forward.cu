@@ -96,12 +96,13 @@ extern "C" int hvlm_vit_l14_layout(int n_layers, hvlm_vit_layout* L) {
 }
 
 namespace hvlm {
-static int g_ln_fold = -1;    // -1: not decided yet (environment), 0 / 1
+static int g_ln_fold = -1;    // -1: not decided yet (environment); 0 off, 1 both LayerNorms, 2 LN1 only, 3 LN2 only
 static int ln_fold_setting() {
     if (g_ln_fold < 0) {
         const char* e = getenv("HVLM_LN_FOLD");
         const char* one = getenv("HVLM_GEMM_1CTA");     // the fold lives in the 2-CTA kernel only
-        g_ln_fold = ((e && e[0] == '0') || (one && one[0] == '1')) ? 0 : 1;
+        int v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 1;
+        g_ln_fold = (one && one[0] == '1') ? 0 : v;
     }
     return g_ln_fold;
 }
@@ -111,7 +112,7 @@ extern "C" int hvlm_vit_set_ln_fold(int on) {
     const int prev = hvlm::ln_fold_setting();
     if (on >= 0) {
         const char* one = getenv("HVLM_GEMM_1CTA");
-        hvlm::g_ln_fold = (on != 0 && !(one && one[0] == '1')) ? 1 : 0;
+        hvlm::g_ln_fold = (one && one[0] == '1') ? 0 : (on <= 3 ? on : 1);
     }
     return prev;
 }
@@ -162,7 +163,11 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         const char* e = getenv("HVLM_LN_FUSION");
         return e && e[0] == '1';
     }();
-    const bool fold = !fuse_ln && ln_fold_setting() != 0 && n_layers_run > 0;
+    // which of the two LayerNorms of a layer are folded: LN1 (fc2 of the previous layer / pre_layrnorm produce, QKV consumes),
+    // LN2 (out_proj produces, fc1 consumes)
+    const int fold_set = (!fuse_ln && n_layers_run > 0) ? ln_fold_setting() : 0;
+    const bool fold1 = fold_set == 1 || fold_set == 2, fold2 = fold_set == 1 || fold_set == 3;
+    const bool fold = fold1 || fold2;
     // tile traversal directions of the four layer GEMMs (bit 0 QKV, 1 out_proj, 2 fc1, 3 fc2: 1 = last-to-first); A/B switch
     static const int rev_mask = []() {
         const char* e = getenv("HVLM_GEMM_REV_MASK");
@@ -195,30 +200,30 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
         // + position embedding (tokens 1..256; the CLS row got pos[0] from im2col), then pre_layrnorm, in place
         // (folded LayerNorms: it also writes the bf16 rows + row statistics the first QKV GEMM consumes)
         rc = launch_layernorm(hidden, f32(L.pre_ln_g), f32(L.pre_ln_b), hidden, M, HVLM_F32, 1e-5f, s, 1, f32(L.pos),
-                              HVLM_VIT_TOKENS, fold ? w8 + ws.y : nullptr, fold ? stats : nullptr, fold ? shift : nullptr);
+                              HVLM_VIT_TOKENS, fold ? w8 + ws.y : nullptr, fold ? stats : nullptr, fold ? shift : nullptr);   // (shift: any fold)
     }
     if (rc) return rc;
 
     for (int l = 0; l < n_layers_run; ++l) {
         const auto& y = L.layer[l];
         const auto& yf = L.fold[l];
-        if (!fold && (!fuse_ln || l == 0)) {   // with fusion, LN1 of layer l > 0 was produced by fc2 of layer l-1
+        if (!fold1 && (!fuse_ln || l == 0)) {   // with fusion, LN1 of layer l > 0 was produced by fc2 of layer l-1
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln1_g), f32(y.ln1_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 0);
             if (rc) return rc;
         }
         {
             EpiArgs ep;
-            ep.bias = f32(fold ? yf.b_qkv_f : y.b_qkv);
+            ep.bias = f32(fold1 ? yf.b_qkv_f : y.b_qkv);
             ep.out = w8 + ws.qkv;
             ep.reverse = rev_mask & 1;
-            if (fold) {      // LN1 folded in: A = bf16 residual rows, B = gamma-scaled weights
+            if (fold1) {      // LN1 folded in: A = bf16 residual rows, B = gamma-scaled weights
                 ep.ln_c = f32(yf.c_qkv);
                 ep.ln_stats = stats;
                 ep.shift_io = shift;
             }
             StageTimer st(HVLM_STAGE_QKV_GEMM, s);
-            rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + (fold ? yf.w_qkv_f : y.w_qkv), M, 3072, 1024, ep, s);
+            rc = launch_gemm(EPI_QKV_HM, w8 + ws.y, wb + (fold1 ? yf.w_qkv_f : y.w_qkv), M, 3072, 1024, ep, s);
             if (rc) return rc;
         }
         {
@@ -238,7 +243,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
                 ep.ln_out = w8 + ws.y;
                 ep.ln_count = ln_count;
             }
-            if (fold) {      // feeds the folded LN2 of fc1
+            if (fold2) {      // feeds the folded LN2 of fc1
                 ep.xb_out = w8 + ws.y;
                 ep.stats_out = stats;
                 ep.shift_in = shift;
@@ -247,23 +252,23 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
             rc = launch_gemm(EPI_RESID_F32, w8 + ws.attn, wb + y.w_o, M, 1024, 1024, ep, s);
             if (rc) return rc;
         }
-        if (!fuse_ln && !fold) {
+        if (!fuse_ln && !fold2) {
             StageTimer st(HVLM_STAGE_LAYERNORM, s);
             rc = launch_layernorm(hidden, f32(y.ln2_g), f32(y.ln2_b), w8 + ws.y, M, HVLM_BF16, 1e-5f, s, 1);
             if (rc) return rc;
         }
         {
             EpiArgs ep;
-            ep.bias = f32(fold ? yf.b_fc1_f : y.b_fc1);
+            ep.bias = f32(fold2 ? yf.b_fc1_f : y.b_fc1);
             ep.out = w8 + ws.f1;
             ep.reverse = (rev_mask >> 2) & 1;
-            if (fold) {
+            if (fold2) {
                 ep.ln_c = f32(yf.c_fc1);
                 ep.ln_stats = stats;
                 ep.shift_io = shift;
             }
             StageTimer st(HVLM_STAGE_FC1_GEMM, s);
-            rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + (fold ? yf.w_fc1_f : y.w_fc1), M, 4096, 1024, ep, s);
+            rc = launch_gemm(EPI_GELU_BF16, w8 + ws.y, wb + (fold2 ? yf.w_fc1_f : y.w_fc1), M, 4096, 1024, ep, s);
             if (rc) return rc;
         }
         if (open_last_mlp && l + 1 == n_layers_run) break;   // the caller applies fc2 after pooling (it is linear)
@@ -279,7 +284,7 @@ static int vit_l14_fwd_impl(const void* weight_blob, int n_layers_run, const voi
                 ep.ln_out = w8 + ws.y;
                 ep.ln_count = ln_count;
             }
-            if (fold && l + 1 < n_layers_run) {      // feeds the folded LN1 of the next layer (nobody reads them after the last)
+            if (fold1 && l + 1 < n_layers_run) {      // feeds the folded LN1 of the next layer (nobody reads them after the last)
                 ep.xb_out = w8 + ws.y;
                 ep.stats_out = stats;
                 ep.shift_in = shift;

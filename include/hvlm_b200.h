@@ -166,8 +166,9 @@ HVLM_API int hvlm_vit_l14_fwd_open_mlp(const void* weight_blob, int n_layers_run
 /* hidden f32 [n,257,1024] -> feats [n,256,1024] (drop CLS) cast to out_dtype (clip_encoder.py:31-32,49). */
 HVLM_API int hvlm_feature_select(const float* hidden, void* feats, int n_frames, int out_dtype, int keep_cls, void* stream);
 
-/* The tower runs with its 46 per-layer LayerNorm launches folded into the GEMMs around them (default; the environment
- * variable HVLM_LN_FOLD=0 or this call with on = 0 restores the stand-alone LayerNorm kernels; on < 0 only queries).
+/* The tower runs with its 46 per-layer LayerNorm launches folded into the GEMMs around them (default = 1; the environment
+ * variable HVLM_LN_FOLD=0 or this call with on = 0 restores the stand-alone LayerNorm kernels; 2 / 3 fold only LayerNorm 1
+ * (fc2 -> QKV) / only LayerNorm 2 (out_proj -> fc1), for A/B runs; on < 0 only queries).
  * Process-wide switch, returns the previous setting.  Both settings produce the same tower within bf16-operand rounding
  * (same operand precision: the GEMM reads bf16(x) and bf16(gamma*W) instead of bf16(LN(x)) and bf16(W)). */
 HVLM_API int hvlm_vit_set_ln_fold(int on);
